@@ -1,0 +1,517 @@
+// C ABI of libmdil_b200.so (declared in include/mdil_b200.h): argument checking and the per-block
+// launch sequences.  No device allocation, no global mutable device state, everything asynchronous
+// on the caller's stream.
+#include "../../include/mdil_b200.h"
+#include "kernels.cuh"
+
+#include <atomic>
+#include <stdio.h>
+#include <string.h>
+
+namespace mdil {
+
+static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+int set_error(int code, const char* what, const char* file, int line) {
+  const char* base = strrchr(file, '/');
+  snprintf(g_err, sizeof(g_err), "mdil_b200 error %d: %s (%s:%d)", code, what, base ? base + 1 : file, line);
+  return code == 0 ? -1 : code;
+}
+
+namespace {
+
+inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+struct Carver {
+  unsigned char* base;
+  size_t off;
+  explicit Carver(void* p) : base(static_cast<unsigned char*>(p)), off(0) {}
+  template <typename T> T* take(size_t n) {
+    off = align_up(off, 256);
+    T* r = reinterpret_cast<T*>(base + off);
+    off += n * sizeof(T);
+    return r;
+  }
+};
+
+// 3-tap conv along rows (vert) or columns, dilation d, NHWC [N,H,W,C] -> same shape.
+ConvGeom taps3_geom(int N, int H, int W, int C, int d, bool vert) {
+  ConvGeom g;
+  memset(&g, 0, sizeof(g));
+  g.N = N; g.VH = H; g.VW = W;
+  g.AH = H; g.AW = W; g.lda = C; g.a_coff = 0; g.a_sy = 1; g.a_sx = 1;
+  g.GH = H; g.GW = W; g.ldg = C; g.g_coff = 0; g.g_sy = 1; g.g_sx = 1;
+  g.CIN = C; g.COUT = C; g.COUT_PAD = C; g.CIN_VALID = C;
+  g.nclasses = 1;
+  g.cls[0].ntaps = 3;
+  for (int k = 0; k < 3; ++k) {
+    g.cls[0].a_dy[k] = vert ? (k - 1) * d : 0;
+    g.cls[0].a_dx[k] = vert ? 0 : (k - 1) * d;
+    g.cls[0].widx[k] = k;
+  }
+  return g;
+}
+
+ConvGeom pointwise_geom(int N, int H, int W, int C) {
+  ConvGeom g = taps3_geom(N, H, W, C, 1, true);
+  g.cls[0].ntaps = 1;
+  g.cls[0].a_dy[0] = 0; g.cls[0].a_dx[0] = 0; g.cls[0].widx[0] = 0;
+  return g;
+}
+
+// Sub-pixel parity classes of a 3x3 stride-2 pad-1 (output_padding 1) transposed convolution:
+// fine coordinate 2v+p receives kernel index 1 from coarse v (p = 0) or indices 0 / 2 from coarse v+1 / v (p = 1).
+void fill_parity_classes(ConvGeom& g) {
+  g.nclasses = 4;
+  for (int py = 0; py < 2; ++py)
+    for (int px = 0; px < 2; ++px) {
+      TapClass& tc = g.cls[py * 2 + px];
+      tc.o_dy = py; tc.o_dx = px;
+      int ny = py ? 2 : 1, nx = px ? 2 : 1;
+      const int kys[2] = {py ? 0 : 1, 2}, dys[2] = {py ? 1 : 0, 0};
+      const int kxs[2] = {px ? 0 : 1, 2}, dxs[2] = {px ? 1 : 0, 0};
+      int t = 0;
+      for (int a = 0; a < ny; ++a)
+        for (int b = 0; b < nx; ++b) {
+          tc.a_dy[t] = dys[a]; tc.a_dx[t] = dxs[b]; tc.widx[t] = kys[a] * 3 + kxs[b];
+          ++t;
+        }
+      tc.ntaps = t;
+    }
+}
+
+void fill_3x3_taps(ConvGeom& g) {
+  g.nclasses = 1;
+  TapClass& tc = g.cls[0];
+  tc.ntaps = 9; tc.o_dy = 0; tc.o_dx = 0;
+  for (int ky = 0; ky < 3; ++ky)
+    for (int kx = 0; kx < 3; ++kx) {
+      tc.a_dy[ky * 3 + kx] = ky - 1; tc.a_dx[ky * 3 + kx] = kx - 1; tc.widx[ky * 3 + kx] = ky * 3 + kx;
+    }
+}
+
+int check_nb1d(const mdil_nb1d_desc* d) {
+  MDIL_REQUIRE(d != nullptr, "nb1d: null descriptor");
+  MDIL_REQUIRE(d->C == 16 || d->C == 64 || d->C == 128, "nb1d: C must be 16, 64 or 128");
+  MDIL_REQUIRE(d->N > 0 && d->H > 0 && d->W > 0 && d->dil >= 1, "nb1d: bad dims");
+  return 0;
+}
+
+}  // namespace
+}  // namespace mdil
+
+using namespace mdil;
+
+extern "C" {
+
+const char* mdil_version(void) { return "mdil_b200 0.1 (sm_100a)"; }
+const char* mdil_last_error_string(void) { return mdil::g_err; }
+unsigned long long mdil_launch_count(void) { return mdil::g_launches.load(std::memory_order_relaxed); }
+
+int mdil_device_supported(int device) {
+  cudaDeviceProp p;
+  if (cudaGetDeviceProperties(&p, device) != cudaSuccess) return 0;
+  return p.major == 10 ? 1 : 0;
+}
+
+int mdil_nchw_to_nhwc4(const float* x, float* y, int N, int C, int H, int W, void* stream) {
+  return launch_nchw_to_nhwc4(x, y, N, C, H, W, S(stream));
+}
+
+// =============================================================================== nb1d
+size_t mdil_nb1d_packed_floats(int C) { return (size_t)28 * C * C; }
+
+size_t mdil_nb1d_fwd_workspace_bytes(const mdil_nb1d_desc* d) { return 256 + (size_t)4 * d->C * sizeof(double) + 256; }
+
+size_t mdil_nb1d_bwd_workspace_bytes(const mdil_nb1d_desc* d) {
+  size_t T = align_up((size_t)d->N * d->H * d->W * d->C * sizeof(float), 256);
+  return 3 * T + (size_t)4 * d->C * sizeof(double) + (size_t)6 * d->C * sizeof(float) + 8 * 256;
+}
+
+int mdil_nb1d_pack(const mdil_nb1d_desc* d, const mdil_nb1d_weights* w, float* packed, void* stream) {
+  MDIL_TRY(check_nb1d(d));
+  const int C = d->C;
+  const long CC = (long)C * C;
+  cudaStream_t s = S(stream);
+  // forward streams: slab[k][ci][co] = W[co][ci][k]
+  MDIL_TRY(launch_pack(w->w31_1, packed + 0 * CC, 3, C, C, C, C, 3, 3L * C, 1, 0, s));
+  MDIL_TRY(launch_pack(w->w13_1, packed + 3 * CC, 3, C, C, C, C, 3, 3L * C, 1, 0, s));
+  MDIL_TRY(launch_pack(w->w31_2, packed + 7 * CC, 3, C, C, C, C, 3, 3L * C, 1, 0, s));
+  MDIL_TRY(launch_pack(w->w13_2, packed + 10 * CC, 3, C, C, C, C, 3, 3L * C, 1, 0, s));
+  // backward streams (second conv first, taps flipped): slab[k'][co][ci] = W[co][ci][2-k']
+  MDIL_TRY(launch_pack(w->w13_2, packed + 14 * CC, 3, C, C, C, C, 3L * C, 3, 1, 1, s));
+  MDIL_TRY(launch_pack(w->w31_2, packed + 17 * CC, 3, C, C, C, C, 3L * C, 3, 1, 1, s));
+  MDIL_TRY(launch_pack(w->w13_1, packed + 21 * CC, 3, C, C, C, C, 3L * C, 3, 1, 1, s));
+  MDIL_TRY(launch_pack(w->w31_1, packed + 24 * CC, 3, C, C, C, C, 3L * C, 3, 1, 1, s));
+  if (d->has_adapter) {
+    MDIL_REQUIRE(w->wp1 != nullptr && w->wp2 != nullptr, "nb1d: adapter weights missing");
+    MDIL_TRY(launch_pack(w->wp1, packed + 6 * CC, 1, C, C, C, C, 1, C, 0, 0, s));    // [ci][co] = Wp[co][ci]
+    MDIL_TRY(launch_pack(w->wp2, packed + 13 * CC, 1, C, C, C, C, 1, C, 0, 0, s));
+    MDIL_TRY(launch_pack(w->wp2, packed + 20 * CC, 1, C, C, C, C, C, 1, 0, 0, s));   // [co][ci]
+    MDIL_TRY(launch_pack(w->wp1, packed + 27 * CC, 1, C, C, C, C, C, 1, 0, 0, s));
+  }
+  return 0;
+}
+
+int mdil_nb1d_fwd(const mdil_nb1d_desc* d, const float* x, const mdil_nb1d_weights* w, const float* packed,
+                  const float* drop_mask, float* y, const mdil_nb1d_saved* sv, void* ws, size_t ws_bytes, void* stream) {
+  MDIL_TRY(check_nb1d(d));
+  MDIL_REQUIRE(ws_bytes >= mdil_nb1d_fwd_workspace_bytes(d), "nb1d_fwd: workspace too small");
+  MDIL_REQUIRE(sv != nullptr && sv->p != nullptr && sv->s != nullptr && sv->stats != nullptr, "nb1d_fwd: p/s/stats buffers required");
+  const int C = d->C;
+  const long CC = (long)C * C;
+  const size_t HW = (size_t)d->H * d->W;
+  const double count = (double)d->N * (double)HW;
+  cudaStream_t s = S(stream);
+  Carver cv(ws);
+  double* sums1 = cv.take<double>(2 * C);
+  double* sums2 = cv.take<double>(2 * C);
+  float* st1 = sv->stats;
+  float* st2 = sv->stats + 4 * C;
+  if (d->train) {
+    MDIL_CUDA(cudaMemsetAsync(sums1, 0, 2 * C * sizeof(double), s));
+    MDIL_CUDA(cudaMemsetAsync(sums2, 0, 2 * C * sizeof(double), s));
+  }
+  PairArgs a;
+  memset(&a, 0, sizeof(a));
+  a.N = d->N; a.H = d->H; a.W = d->W; a.C = C; a.has_adapter = d->has_adapter; a.vert_first = 1; a.epi = kEpiFwd;
+  // pair 1: x -> a -> p
+  a.in = x; a.wstream = packed; a.b1 = w->b31_1; a.b2 = w->b13_1; a.bad = d->has_adapter ? w->bp1 : nullptr;
+  a.mid_out = d->save ? sv->a : nullptr; a.out = sv->p; a.sums = d->train ? sums1 : nullptr; a.dil = 1;
+  MDIL_TRY(launch_pair(a, s));
+  MDIL_TRY(launch_bn_finalize(sums1, C, count, C, w->bn1.weight, w->bn1.bias, w->bn1.running_mean, w->bn1.running_var,
+                              d->eps, d->momentum, d->train, st1, s));
+  // pair 2: r = relu(bn1(p)) -> c -> s
+  a.in = sv->p; a.in_scale = st1 + 2 * C; a.in_shift = st1 + 3 * C; a.wstream = packed + 7 * CC;
+  a.b1 = w->b31_2; a.b2 = w->b13_2; a.bad = d->has_adapter ? w->bp2 : nullptr;
+  a.mid_out = d->save ? sv->c : nullptr; a.out = sv->s; a.sums = d->train ? sums2 : nullptr; a.dil = d->dil;
+  MDIL_TRY(launch_pair(a, s));
+  MDIL_TRY(launch_bn_finalize(sums2, C, count, C, w->bn2.weight, w->bn2.bias, w->bn2.running_mean, w->bn2.running_var,
+                              d->eps, d->momentum, d->train, st2, s));
+  // y = relu(bn2(s) * drop + x)
+  MDIL_TRY(launch_bn_act(sv->s, st2, drop_mask, x, y, d->N, HW, C, s));
+  return 0;
+}
+
+static int nb1d_wgrad(const ConvGeom& g, const float* A, const float* sc, const float* sh, const float* G, float* dW,
+                      float* db, int C, int taps, cudaStream_t s) {
+  if (dW == nullptr) {
+    MDIL_REQUIRE(db == nullptr, "nb1d_bwd: bias gradient without weight gradient is not supported");
+    return 0;
+  }
+  MDIL_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)C * C * taps, s));
+  if (db != nullptr) MDIL_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * C, s));
+  // torch layout [co][ci][taps]
+  return launch_wgrad_taps(g, A, sc, sh, G, dW, taps, (long)C * taps, taps == 1 ? 0 : 1, db, s);
+}
+
+int mdil_nb1d_bwd(const mdil_nb1d_desc* d, const float* dy, const float* x, const float* y, const mdil_nb1d_weights* w,
+                  const float* packed, const float* drop_mask, const mdil_nb1d_saved* sv, float* dx,
+                  const mdil_nb1d_grads* gr, void* ws, size_t ws_bytes, void* stream) {
+  MDIL_TRY(check_nb1d(d));
+  MDIL_REQUIRE(d->train, "nb1d_bwd: backward is only implemented for train-mode BatchNorm (batch statistics)");
+  MDIL_REQUIRE(ws_bytes >= mdil_nb1d_bwd_workspace_bytes(d), "nb1d_bwd: workspace too small");
+  MDIL_REQUIRE(sv != nullptr && sv->a && sv->p && sv->c && sv->s && sv->stats, "nb1d_bwd: saved tensors missing");
+  MDIL_REQUIRE(dx != nullptr && gr != nullptr, "nb1d_bwd: dx/grads required");
+  const int C = d->C, N = d->N, H = d->H, W = d->W;
+  const long CC = (long)C * C;
+  const size_t HW = (size_t)H * W;
+  const size_t T = (size_t)N * HW * C;
+  const double count = (double)N * (double)HW;
+  cudaStream_t s = S(stream);
+  Carver cv(ws);
+  double* sums2 = cv.take<double>(2 * C);
+  double* sums1 = cv.take<double>(2 * C);
+  float* coef2 = cv.take<float>(3 * C);
+  float* coef1 = cv.take<float>(3 * C);
+  float* T1 = cv.take<float>(T);
+  float* T2 = cv.take<float>(T);
+  float* T3 = cv.take<float>(T);
+  const float* st1 = sv->stats;
+  const float* st2 = sv->stats + 4 * C;
+  MDIL_CUDA(cudaMemsetAsync(sums2, 0, 2 * C * sizeof(double), s));
+  MDIL_CUDA(cudaMemsetAsync(sums1, 0, 2 * C * sizeof(double), s));
+
+  // ---- BN2 backward (+ ReLU mask of y, dropout): ds
+  MDIL_TRY(launch_bn_bwd_stats(dy, y, drop_mask, sv->s, st2, sums2, N, HW, C, s));
+  MDIL_TRY(launch_bn_bwd_finalize(sums2, count, C, w->bn2.weight, st2, coef2, gr->bn2_w, gr->bn2_b, s));
+  MDIL_TRY(launch_bn_bwd_apply(dy, y, drop_mask, sv->s, st2, coef2, T1, N, HW, C, s));
+
+  // ---- pair 2 backward: ds -> dc' -> dq (masked by r>0), sums for BN1 backward
+  PairArgs a;
+  memset(&a, 0, sizeof(a));
+  a.N = N; a.H = H; a.W = W; a.C = C; a.has_adapter = d->has_adapter; a.vert_first = 0;
+  a.in = T1; a.wstream = packed + 14 * CC; a.mid_mask = sv->c; a.mid_out = T2; a.out = T3;
+  a.epi = kEpiBwdMaskStats; a.e0 = sv->p; a.e_stats = st1; a.sums = sums1; a.dil = d->dil;
+  MDIL_TRY(launch_pair(a, s));
+
+  // ---- weight gradients of pair 2
+  {
+    ConvGeom gh = taps3_geom(N, H, W, C, d->dil, false), gv = taps3_geom(N, H, W, C, d->dil, true);
+    ConvGeom gp = pointwise_geom(N, H, W, C);
+    MDIL_TRY(nb1d_wgrad(gh, sv->c, nullptr, nullptr, T1, gr->w13_2, gr->b13_2, C, 3, s));
+    if (d->has_adapter) MDIL_TRY(nb1d_wgrad(gp, sv->p, st1 + 2 * C, st1 + 3 * C, T1, gr->wp2, gr->bp2, C, 1, s));
+    MDIL_TRY(nb1d_wgrad(gv, sv->p, st1 + 2 * C, st1 + 3 * C, T2, gr->w31_2, gr->b31_2, C, 3, s));
+  }
+
+  // ---- BN1 backward: dq -> dp (overwrites ds)
+  MDIL_TRY(launch_bn_bwd_finalize(sums1, count, C, w->bn1.weight, st1, coef1, gr->bn1_w, gr->bn1_b, s));
+  MDIL_TRY(launch_bn_bwd_apply(T3, nullptr, nullptr, sv->p, st1, coef1, T1, N, HW, C, s));
+
+  // ---- pair 1 backward: dp -> da' -> dx (+ residual dy * (y>0))
+  a.in = T1; a.wstream = packed + 21 * CC; a.mid_mask = sv->a; a.mid_out = T2; a.out = dx;
+  a.epi = kEpiBwdResidual; a.e0 = dy; a.e1 = y; a.e_stats = nullptr; a.sums = nullptr; a.dil = 1;
+  MDIL_TRY(launch_pair(a, s));
+
+  // ---- weight gradients of pair 1
+  {
+    ConvGeom gh = taps3_geom(N, H, W, C, 1, false), gv = taps3_geom(N, H, W, C, 1, true);
+    ConvGeom gp = pointwise_geom(N, H, W, C);
+    MDIL_TRY(nb1d_wgrad(gh, sv->a, nullptr, nullptr, T1, gr->w13_1, gr->b13_1, C, 3, s));
+    if (d->has_adapter) MDIL_TRY(nb1d_wgrad(gp, x, nullptr, nullptr, T1, gr->wp1, gr->bp1, C, 1, s));
+    MDIL_TRY(nb1d_wgrad(gv, x, nullptr, nullptr, T2, gr->w31_1, gr->b31_1, C, 3, s));
+  }
+  return 0;
+}
+
+// =============================================================================== downsampler
+static inline int down_cinp(const mdil_down_desc* d) { return d->ldin; }
+static inline int down_cconv(const mdil_down_desc* d) { return d->Cout - d->Cin; }
+static inline int down_coutp(const mdil_down_desc* d) { return (down_cconv(d) + 3) / 4 * 4; }
+
+size_t mdil_down_packed_floats(const mdil_down_desc* d) {
+  return (size_t)9 * down_cinp(d) * down_coutp(d) + (size_t)9 * down_cconv(d) * d->Cin + 64;
+}
+
+size_t mdil_down_workspace_bytes(const mdil_down_desc* d) {
+  size_t du = align_up((size_t)d->N * (d->H / 2) * (d->W / 2) * d->Cout * sizeof(float), 256);
+  return du + (size_t)2 * d->Cout * sizeof(double) + (size_t)3 * d->Cout * sizeof(float) + 4 * 256;
+}
+
+static int check_down(const mdil_down_desc* d) {
+  MDIL_REQUIRE(d != nullptr && d->N > 0 && d->H > 0 && d->W > 0 && d->H % 2 == 0 && d->W % 2 == 0, "down: bad dims");
+  MDIL_REQUIRE(d->ldin % 4 == 0 && d->ldin >= d->Cin && d->Cout % 4 == 0 && d->Cout > d->Cin, "down: bad channels");
+  MDIL_REQUIRE(256 % (d->Cout / 4) == 0, "down: unsupported Cout");
+  return 0;
+}
+
+int mdil_down_pack(const mdil_down_desc* d, const float* w, float* packed, void* stream) {
+  MDIL_TRY(check_down(d));
+  const int Cin = d->Cin, Cc = down_cconv(d), CinP = down_cinp(d), CoP = down_coutp(d);
+  cudaStream_t s = S(stream);
+  // forward: slab[t][ci][co] = W[co][ci][t]
+  MDIL_TRY(launch_pack(w, packed, 9, Cin, CinP, Cc, CoP, 9, 9L * Cin, 1, 0, s));
+  // dgrad: slab[t][co][ci] = W[co][ci][t]
+  if (Cin % 4 == 0 && Cc % 4 == 0)
+    MDIL_TRY(launch_pack(w, packed + (size_t)9 * CinP * CoP, 9, Cc, Cc, Cin, Cin, 9L * Cin, 9, 1, 0, s));
+  return 0;
+}
+
+static int bn_forward_tail(const float* u, size_t P, int C, const mdil_bn_params* bn, int train, float eps, float momentum,
+                           double* sums, float* stats, float* y, int N, size_t HW, cudaStream_t s) {
+  if (train) {
+    MDIL_CUDA(cudaMemsetAsync(sums, 0, 2 * C * sizeof(double), s));
+    MDIL_TRY(launch_channel_stats(u, P, C, 0, C, sums, C, s));
+  }
+  MDIL_TRY(launch_bn_finalize(sums, C, (double)P, C, bn->weight, bn->bias, bn->running_mean, bn->running_var, eps,
+                              momentum, train, stats, s));
+  MDIL_TRY(launch_bn_act(u, stats, nullptr, nullptr, y, N, HW, C, s));
+  return 0;
+}
+
+int mdil_down_fwd(const mdil_down_desc* d, const float* x, const float* packed, const float* bias,
+                  const mdil_bn_params* bn, float* u, float* stats, float* y, void* ws, size_t ws_bytes, void* stream) {
+  MDIL_TRY(check_down(d));
+  MDIL_REQUIRE(ws_bytes >= (size_t)2 * d->Cout * sizeof(double) + 512, "down_fwd: workspace too small");
+  cudaStream_t s = S(stream);
+  const int OH = d->H / 2, OW = d->W / 2, Cc = down_cconv(d);
+  ConvGeom g;
+  memset(&g, 0, sizeof(g));
+  g.N = d->N; g.VH = OH; g.VW = OW;
+  g.AH = d->H; g.AW = d->W; g.lda = d->ldin; g.a_coff = 0; g.a_sy = 2; g.a_sx = 2;
+  g.GH = OH; g.GW = OW; g.ldg = d->Cout; g.g_coff = 0; g.g_sy = 1; g.g_sx = 1;
+  g.CIN = down_cinp(d); g.COUT = Cc; g.COUT_PAD = down_coutp(d); g.CIN_VALID = d->Cin;
+  fill_3x3_taps(g);
+  MDIL_TRY(launch_conv_taps(g, x, packed, bias, u, s));
+  MDIL_TRY(launch_pool_fwd(x, u, d->N, d->H, d->W, d->Cin, d->ldin, d->Cout, Cc, s));
+  Carver cv(ws);
+  double* sums = cv.take<double>(2 * d->Cout);
+  return bn_forward_tail(u, (size_t)d->N * OH * OW, d->Cout, bn, d->train, d->eps, d->momentum, sums, stats, y, d->N,
+                         (size_t)OH * OW, s);
+}
+
+int mdil_down_bwd(const mdil_down_desc* d, const float* dy, const float* x, const float* u, const float* y,
+                  const float* stats, const float* packed, const mdil_bn_params* bn, float* dx, float* dw, float* db,
+                  float* dgamma, float* dbeta, void* ws, size_t ws_bytes, void* stream) {
+  MDIL_TRY(check_down(d));
+  MDIL_REQUIRE(d->train, "down_bwd: backward is only implemented for train-mode BatchNorm");
+  MDIL_REQUIRE(ws_bytes >= mdil_down_workspace_bytes(d), "down_bwd: workspace too small");
+  cudaStream_t s = S(stream);
+  const int OH = d->H / 2, OW = d->W / 2, Cc = down_cconv(d), Cout = d->Cout, Cin = d->Cin;
+  const size_t OHW = (size_t)OH * OW;
+  Carver cv(ws);
+  double* sums = cv.take<double>(2 * Cout);
+  float* coef = cv.take<float>(3 * Cout);
+  float* du = cv.take<float>((size_t)d->N * OHW * Cout);
+  MDIL_CUDA(cudaMemsetAsync(sums, 0, 2 * Cout * sizeof(double), s));
+  MDIL_TRY(launch_bn_bwd_stats(dy, y, nullptr, u, stats, sums, d->N, OHW, Cout, s));
+  MDIL_TRY(launch_bn_bwd_finalize(sums, (double)d->N * OHW, Cout, bn->weight, stats, coef, dgamma, dbeta, s));
+  MDIL_TRY(launch_bn_bwd_apply(dy, y, nullptr, u, stats, coef, du, d->N, OHW, Cout, s));
+  if (dw != nullptr) {
+    ConvGeom g;
+    memset(&g, 0, sizeof(g));
+    g.N = d->N; g.VH = OH; g.VW = OW;
+    g.AH = d->H; g.AW = d->W; g.lda = d->ldin; g.a_coff = 0; g.a_sy = 2; g.a_sx = 2;
+    g.GH = OH; g.GW = OW; g.ldg = Cout; g.g_coff = 0; g.g_sy = 1; g.g_sx = 1;
+    g.CIN = down_cinp(d); g.COUT = Cc; g.COUT_PAD = down_coutp(d); g.CIN_VALID = Cin;
+    fill_3x3_taps(g);
+    MDIL_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cc * Cin * 9, s));
+    if (db != nullptr) MDIL_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * Cc, s));
+    MDIL_TRY(launch_wgrad_taps(g, x, nullptr, nullptr, du, dw, 9, 9L * Cin, 1, db, s));  // [co][ci][3][3]
+  } else {
+    MDIL_REQUIRE(db == nullptr, "down_bwd: bias gradient without weight gradient is not supported");
+  }
+  if (dx != nullptr) {
+    MDIL_REQUIRE(Cin % 4 == 0 && Cc % 4 == 0 && d->ldin == Cin, "down_bwd: dx needs Cin % 4 == 0");
+    ConvGeom g;
+    memset(&g, 0, sizeof(g));
+    g.N = d->N; g.VH = OH; g.VW = OW;
+    g.AH = OH; g.AW = OW; g.lda = Cout; g.a_coff = 0; g.a_sy = 1; g.a_sx = 1;
+    g.GH = d->H; g.GW = d->W; g.ldg = Cin; g.g_coff = 0; g.g_sy = 2; g.g_sx = 2;
+    g.CIN = Cc; g.COUT = Cin; g.COUT_PAD = Cin; g.CIN_VALID = Cc;
+    fill_parity_classes(g);
+    MDIL_TRY(launch_conv_taps(g, du, packed + (size_t)9 * down_cinp(d) * down_coutp(d), nullptr, dx, s));
+    MDIL_TRY(launch_pool_bwd(x, du, dx, d->N, d->H, d->W, Cin, d->ldin, Cout, Cc, 1, s));
+  }
+  return 0;
+}
+
+// =============================================================================== upsampler
+size_t mdil_up_packed_floats(const mdil_up_desc* d) { return (size_t)18 * d->Cin * d->Cout + 64; }
+
+size_t mdil_up_workspace_bytes(const mdil_up_desc* d) {
+  size_t du = align_up((size_t)d->N * (2 * d->H) * (2 * d->W) * d->Cout * sizeof(float), 256);
+  return du + (size_t)2 * d->Cout * sizeof(double) + (size_t)3 * d->Cout * sizeof(float) + 4 * 256;
+}
+
+static int check_up(const mdil_up_desc* d) {
+  MDIL_REQUIRE(d != nullptr && d->N > 0 && d->H > 0 && d->W > 0, "up: bad dims");
+  MDIL_REQUIRE(d->Cin % 4 == 0 && d->Cout % 4 == 0 && 256 % (d->Cout / 4) == 0, "up: bad channels");
+  return 0;
+}
+
+int mdil_up_pack(const mdil_up_desc* d, const float* w, float* packed, void* stream) {
+  MDIL_TRY(check_up(d));
+  const int Cin = d->Cin, Cout = d->Cout;
+  cudaStream_t s = S(stream);
+  // forward: slab[t][ci][co] = W[ci][co][t]   (torch ConvTranspose2d layout [Cin][Cout][3][3])
+  MDIL_TRY(launch_pack(w, packed, 9, Cin, Cin, Cout, Cout, 9L * Cout, 9, 1, 0, s));
+  // dgrad: slab[t][co][ci] = W[ci][co][t]
+  MDIL_TRY(launch_pack(w, packed + (size_t)9 * Cin * Cout, 9, Cout, Cout, Cin, Cin, 9, 9L * Cout, 1, 0, s));
+  return 0;
+}
+
+static ConvGeom up_parity_geom(const mdil_up_desc* d) {
+  ConvGeom g;
+  memset(&g, 0, sizeof(g));
+  g.N = d->N; g.VH = d->H; g.VW = d->W;
+  g.AH = d->H; g.AW = d->W; g.lda = d->Cin; g.a_coff = 0; g.a_sy = 1; g.a_sx = 1;
+  g.GH = 2 * d->H; g.GW = 2 * d->W; g.ldg = d->Cout; g.g_coff = 0; g.g_sy = 2; g.g_sx = 2;
+  g.CIN = d->Cin; g.COUT = d->Cout; g.COUT_PAD = d->Cout; g.CIN_VALID = d->Cin;
+  fill_parity_classes(g);
+  return g;
+}
+
+int mdil_up_fwd(const mdil_up_desc* d, const float* x, const float* packed, const float* bias, const mdil_bn_params* bn,
+                float* u, float* stats, float* y, void* ws, size_t ws_bytes, void* stream) {
+  MDIL_TRY(check_up(d));
+  MDIL_REQUIRE(ws_bytes >= (size_t)2 * d->Cout * sizeof(double) + 512, "up_fwd: workspace too small");
+  cudaStream_t s = S(stream);
+  ConvGeom g = up_parity_geom(d);
+  MDIL_TRY(launch_conv_taps(g, x, packed, bias, u, s));
+  Carver cv(ws);
+  double* sums = cv.take<double>(2 * d->Cout);
+  const size_t OHW = (size_t)4 * d->H * d->W;
+  return bn_forward_tail(u, (size_t)d->N * OHW, d->Cout, bn, d->train, d->eps, d->momentum, sums, stats, y, d->N, OHW, s);
+}
+
+int mdil_up_bwd(const mdil_up_desc* d, const float* dy, const float* x, const float* u, const float* y,
+                const float* stats, const float* packed, const mdil_bn_params* bn, float* dx, float* dw, float* db,
+                float* dgamma, float* dbeta, void* ws, size_t ws_bytes, void* stream) {
+  MDIL_TRY(check_up(d));
+  MDIL_REQUIRE(d->train, "up_bwd: backward is only implemented for train-mode BatchNorm");
+  MDIL_REQUIRE(ws_bytes >= mdil_up_workspace_bytes(d), "up_bwd: workspace too small");
+  cudaStream_t s = S(stream);
+  const int Cin = d->Cin, Cout = d->Cout;
+  const size_t OHW = (size_t)4 * d->H * d->W;
+  Carver cv(ws);
+  double* sums = cv.take<double>(2 * Cout);
+  float* coef = cv.take<float>(3 * Cout);
+  float* du = cv.take<float>((size_t)d->N * OHW * Cout);
+  MDIL_CUDA(cudaMemsetAsync(sums, 0, 2 * Cout * sizeof(double), s));
+  MDIL_TRY(launch_bn_bwd_stats(dy, y, nullptr, u, stats, sums, d->N, OHW, Cout, s));
+  MDIL_TRY(launch_bn_bwd_finalize(sums, (double)d->N * OHW, Cout, bn->weight, stats, coef, dgamma, dbeta, s));
+  MDIL_TRY(launch_bn_bwd_apply(dy, y, nullptr, u, stats, coef, du, d->N, OHW, Cout, s));
+  if (dw != nullptr) {
+    ConvGeom g = up_parity_geom(d);
+    MDIL_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cin * Cout * 9, s));
+    if (db != nullptr) MDIL_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * Cout, s));
+    MDIL_TRY(launch_wgrad_taps(g, x, nullptr, nullptr, du, dw, 9L * Cout, 9, 1, db, s));  // [ci][co][3][3]
+  } else {
+    MDIL_REQUIRE(db == nullptr, "up_bwd: bias gradient without weight gradient is not supported");
+  }
+  if (dx != nullptr) {
+    ConvGeom g;
+    memset(&g, 0, sizeof(g));
+    g.N = d->N; g.VH = d->H; g.VW = d->W;
+    g.AH = 2 * d->H; g.AW = 2 * d->W; g.lda = Cout; g.a_coff = 0; g.a_sy = 2; g.a_sx = 2;
+    g.GH = d->H; g.GW = d->W; g.ldg = Cin; g.g_coff = 0; g.g_sy = 1; g.g_sx = 1;
+    g.CIN = Cout; g.COUT = Cin; g.COUT_PAD = Cin; g.CIN_VALID = Cout;
+    fill_3x3_taps(g);
+    MDIL_TRY(launch_conv_taps(g, du, packed + (size_t)9 * Cin * Cout, nullptr, dx, s));
+  }
+  return 0;
+}
+
+// =============================================================================== head + losses
+int mdil_outconv_fwd(const float* x, const float* w, const float* bias, float* logits, int N, int H, int W, int Ccls,
+                     void* stream) {
+  return launch_outconv_fwd(x, w, bias, logits, N, H, W, Ccls, S(stream));
+}
+
+int mdil_outconv_bwd(const float* dlogits, const float* x, const float* w, float* dx, float* dw, float* db, int N,
+                     int H, int W, int Ccls, void* stream) {
+  return launch_outconv_bwd(dlogits, x, w, dx, dw, db, N, H, W, Ccls, S(stream));
+}
+
+int mdil_ce2d_fwd_bwd(const float* logits, const int64_t* labels, const float* class_w, int N, int C, int H, int W,
+                      float* loss, double* acc, float* dlogits, void* stream) {
+  return launch_ce2d(logits, labels, class_w, N, C, H, W, loss, acc, dlogits, S(stream));
+}
+
+int mdil_ce2d_scale(float* dlogits, size_t n, const double* acc, const float* grad_out, void* stream) {
+  return launch_scale(dlogits, n, acc + 1, grad_out, S(stream));
+}
+
+int mdil_kd_fwd_bwd(const float* student, const float* teacher, int N, int C, int H, int W, float* loss, double* acc,
+                    float* dstudent, void* stream) {
+  return launch_kd(student, teacher, N, C, H, W, loss, acc, dstudent, S(stream));
+}
+
+int mdil_scale_by_device_scalar(float* x, size_t n, const float* grad_out, void* stream) {
+  return launch_scale(x, n, nullptr, grad_out, S(stream));
+}
+
+int mdil_argmax_confusion(const float* logits, const int64_t* labels, int N, int C, int H, int W, int64_t* pred,
+                          long long* conf, void* stream) {
+  return launch_argmax_confusion(logits, labels, N, C, H, W, pred, conf, S(stream));
+}
+
+int mdil_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream) {
+  return launch_adam(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, S(stream));
+}
+
+}  // extern "C"

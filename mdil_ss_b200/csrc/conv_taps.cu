@@ -1,0 +1,322 @@
+// Generic gather implicit-GEMM kernels over NHWC fp32 tensors ("tap" formulation):
+//   conv_taps  : out[g(v)] = bias + sum_t A[a_t(v)] . W[widx_t]        (forward / data-gradient)
+//   wgrad_taps : dW[widx_t] += sum_v A[a_t(v)] (x) G[g(v)]             (weight-gradient, + bias gradient)
+// where v walks a virtual pixel grid, a_t(v) = v*a_s + a_d[t] and g(v) = v*g_s + o_d(class).
+// One geometry description covers: the DownsamplerBlock 3x3 stride-2 conv and its dgrad
+// (models/erfnet_RA_parallel.py:17,23), the UpsamplerBlock 3x3 stride-2 transposed conv as four
+// sub-pixel parity classes with 1/2/2/4 taps and its dgrad (:155-156), and every weight gradient.
+// FP32 FFMA register-tiled GEMM (8x4 / TMxTN per thread), operands staged through shared memory.
+#include "kernels.cuh"
+
+namespace mdil {
+
+// ============================================================================ forward / dgrad
+constexpr int CT_M = 128;  // pixels per CTA
+constexpr int CT_N = 64;   // output channels per CTA
+constexpr int CT_K = 16;   // input channels per chunk
+
+__global__ void __launch_bounds__(256)
+conv_taps_kernel(const __grid_constant__ ConvGeom g, const float* __restrict__ A, const float* __restrict__ Wp,
+                 const float* __restrict__ bias, float* __restrict__ out) {
+  __shared__ __align__(16) float As[CT_K][CT_M + 4];
+  __shared__ __align__(16) float Bs[CT_K][CT_N];
+  const TapClass& tc = g.cls[blockIdx.z];
+  const int tid = threadIdx.x;
+  const int tn = tid & 15, tm = tid >> 4;
+  const int lm = tid & 127, lq = tid >> 7;
+  const size_t P = (size_t)g.N * g.VH * g.VW;
+  const size_t lp = (size_t)blockIdx.x * CT_M + lm;
+  const bool lvalid = lp < P;
+  int ln = 0, lvy = 0, lvx = 0;
+  if (lvalid) {
+    lvx = (int)(lp % g.VW);
+    size_t t = lp / g.VW;
+    lvy = (int)(t % g.VH);
+    ln = (int)(t / g.VH);
+  }
+  const int n0 = blockIdx.y * CT_N;
+  const int brow = tid >> 4, bcol = (tid & 15) * 4;
+
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int t = 0; t < tc.ntaps; ++t) {
+    const int ay = lvy * g.a_sy + tc.a_dy[t], ax = lvx * g.a_sx + tc.a_dx[t];
+    const bool inb = lvalid && ay >= 0 && ay < g.AH && ax >= 0 && ax < g.AW;
+    const float* arow = A + (((size_t)ln * g.AH + (inb ? ay : 0)) * g.AW + (inb ? ax : 0)) * g.lda + g.a_coff;
+    const float* wslab = Wp + (size_t)tc.widx[t] * g.CIN * g.COUT_PAD;
+    for (int c0 = 0; c0 < g.CIN; c0 += CT_K) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int q = lq + 2 * h;
+        const int k = c0 + 4 * q;
+        float4 v = make4(0.f);
+        if (inb && k < g.CIN) v = ldg4(arow + k);
+        As[4 * q + 0][lm] = v.x;
+        As[4 * q + 1][lm] = v.y;
+        As[4 * q + 2][lm] = v.z;
+        As[4 * q + 3][lm] = v.w;
+      }
+      {
+        const int kb = c0 + brow, co = n0 + bcol;
+        float4 v = make4(0.f);
+        if (kb < g.CIN && co < g.COUT_PAD) v = ldg4(wslab + (size_t)kb * g.COUT_PAD + co);
+        *reinterpret_cast<float4*>(&Bs[brow][bcol]) = v;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < CT_K; ++k) {
+        const float4 a0 = *reinterpret_cast<const float4*>(&As[k][tm * 8]);
+        const float4 a1 = *reinterpret_cast<const float4*>(&As[k][tm * 8 + 4]);
+        const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tn * 4]);
+        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          acc[i][0] = fmaf(a[i], b.x, acc[i][0]);
+          acc[i][1] = fmaf(a[i], b.y, acc[i][1]);
+          acc[i][2] = fmaf(a[i], b.z, acc[i][2]);
+          acc[i][3] = fmaf(a[i], b.w, acc[i][3]);
+        }
+      }
+      __syncthreads();
+    }
+  }
+
+  const int co = n0 + tn * 4;
+  if (co >= g.COUT) return;
+  float bv[4] = {0.f, 0.f, 0.f, 0.f};
+  if (bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (co + j < g.COUT) bv[j] = __ldg(bias + co + j);
+  }
+  const bool vec = ((g.ldg | g.g_coff) & 3) == 0 && co + 3 < g.COUT;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const size_t p = (size_t)blockIdx.x * CT_M + tm * 8 + i;
+    if (p >= P) continue;
+    const int vx = (int)(p % g.VW);
+    const size_t tt = p / g.VW;
+    const int vy = (int)(tt % g.VH);
+    const int n = (int)(tt / g.VH);
+    const int oy = vy * g.g_sy + tc.o_dy, ox = vx * g.g_sx + tc.o_dx;
+    if (oy < 0 || oy >= g.GH || ox < 0 || ox >= g.GW) continue;
+    float* o = out + (((size_t)n * g.GH + oy) * g.GW + ox) * g.ldg + g.g_coff + co;
+    if (vec) {
+      *reinterpret_cast<float4*>(o) = make_float4(acc[i][0] + bv[0], acc[i][1] + bv[1], acc[i][2] + bv[2], acc[i][3] + bv[3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (co + j < g.COUT) o[j] = acc[i][j] + bv[j];
+    }
+  }
+}
+
+int launch_conv_taps(const ConvGeom& g, const float* A, const float* Wp, const float* bias, float* out, cudaStream_t s) {
+  MDIL_REQUIRE(g.CIN % 4 == 0 && g.lda % 4 == 0 && g.a_coff % 4 == 0 && g.COUT_PAD % 4 == 0, "conv_taps: alignment");
+  MDIL_REQUIRE(g.nclasses >= 1 && g.nclasses <= kMaxClasses, "conv_taps: classes");
+  size_t P = (size_t)g.N * g.VH * g.VW;
+  dim3 grid((unsigned)((P + CT_M - 1) / CT_M), (unsigned)cdiv(g.COUT, CT_N), (unsigned)g.nclasses);
+  conv_taps_kernel<<<grid, 256, 0, s>>>(g, A, Wp, bias, out);
+  MDIL_LAUNCH_CHECK();
+  return 0;
+}
+
+// ============================================================================ weight gradient
+template <int T>
+__device__ __forceinline__ void load_frag(const float* row, int t, float (&f)[T]) {
+  if constexpr (T == 1) {
+    f[0] = row[t];
+  } else if constexpr (T == 4) {
+    const float4 v = *reinterpret_cast<const float4*>(row + t * 4);
+    f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+  } else {
+    const float4 v = *reinterpret_cast<const float4*>(row + t * 4);
+    const float4 w = *reinterpret_cast<const float4*>(row + 64 + t * 4);
+    f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+    f[4] = w.x; f[5] = w.y; f[6] = w.z; f[7] = w.w;
+  }
+}
+template <int T>
+__device__ __forceinline__ int frag_index(int t, int i) {
+  if constexpr (T == 8) return i < 4 ? t * 4 + i : 64 + t * 4 + (i - 4);
+  return t * T + i;
+}
+
+template <int TMW, int TNW, int KP>
+__global__ void __launch_bounds__(256)
+wgrad_taps_kernel(const __grid_constant__ ConvGeom g, const float* __restrict__ A, const float* __restrict__ a_scale,
+                  const float* __restrict__ a_shift, const float* __restrict__ G, float* __restrict__ dW, long s_ci,
+                  long s_co, long s_t, float* __restrict__ db, int pixels_per_cta) {
+  constexpr int CI_TILE = 16 * TMW, CO_TILE = 16 * TNW;
+  __shared__ __align__(16) float As[KP][CI_TILE];
+  __shared__ __align__(16) float Gs[KP][CO_TILE];
+  int cls = 0, t = blockIdx.y;
+  while (t >= g.cls[cls].ntaps) { t -= g.cls[cls].ntaps; ++cls; }
+  const TapClass& tc = g.cls[cls];
+  const int ci_tiles = (g.CIN + CI_TILE - 1) / CI_TILE;
+  const int ci0 = (blockIdx.z % ci_tiles) * CI_TILE, co0 = (blockIdx.z / ci_tiles) * CO_TILE;
+  const int tid = threadIdx.x, tn = tid & 15, tm = tid >> 4;
+  const size_t P = (size_t)g.N * g.VH * g.VW;
+  const size_t p_begin = (size_t)blockIdx.x * pixels_per_cta;
+  const size_t p_end = p_begin + pixels_per_cta < P ? p_begin + pixels_per_cta : P;
+  const bool do_bias = db != nullptr && t == 0 && ci0 == 0 && tm == 0;
+
+  float acc[TMW][TNW];
+  float bsum[TNW];
+#pragma unroll
+  for (int i = 0; i < TMW; ++i)
+#pragma unroll
+    for (int j = 0; j < TNW; ++j) acc[i][j] = 0.f;
+#pragma unroll
+  for (int j = 0; j < TNW; ++j) bsum[j] = 0.f;
+
+  for (size_t p0 = p_begin; p0 < p_end; p0 += KP) {
+    for (int idx = tid; idx < KP * (CI_TILE / 4); idx += 256) {
+      const int kp = idx / (CI_TILE / 4), f4 = idx % (CI_TILE / 4);
+      const size_t p = p0 + kp;
+      const int ci = ci0 + f4 * 4;
+      float4 v = make4(0.f);
+      if (p < p_end && ci < g.CIN) {
+        const int vx = (int)(p % g.VW);
+        const size_t tt = p / g.VW;
+        const int vy = (int)(tt % g.VH);
+        const int n = (int)(tt / g.VH);
+        const int ay = vy * g.a_sy + tc.a_dy[t], ax = vx * g.a_sx + tc.a_dx[t];
+        if (ay >= 0 && ay < g.AH && ax >= 0 && ax < g.AW) {
+          v = ldg4(A + (((size_t)n * g.AH + ay) * g.AW + ax) * g.lda + g.a_coff + ci);
+          if (a_scale != nullptr) {
+            const float4 sc = ldg4(a_scale + ci), sh = ldg4(a_shift + ci);
+            v.x = fmaxf(fmaf(v.x, sc.x, sh.x), 0.f);
+            v.y = fmaxf(fmaf(v.y, sc.y, sh.y), 0.f);
+            v.z = fmaxf(fmaf(v.z, sc.z, sh.z), 0.f);
+            v.w = fmaxf(fmaf(v.w, sc.w, sh.w), 0.f);
+          }
+        }
+      }
+      *reinterpret_cast<float4*>(&As[kp][f4 * 4]) = v;
+    }
+    for (int idx = tid; idx < KP * (CO_TILE / 4); idx += 256) {
+      const int kp = idx / (CO_TILE / 4), f4 = idx % (CO_TILE / 4);
+      const size_t p = p0 + kp;
+      const int co = co0 + f4 * 4;
+      float4 v = make4(0.f);
+      if (p < p_end && co < g.COUT) {
+        const int vx = (int)(p % g.VW);
+        const size_t tt = p / g.VW;
+        const int vy = (int)(tt % g.VH);
+        const int n = (int)(tt / g.VH);
+        const int gy = vy * g.g_sy + tc.o_dy, gx = vx * g.g_sx + tc.o_dx;
+        if (gy >= 0 && gy < g.GH && gx >= 0 && gx < g.GW)
+          v = ldg4(G + (((size_t)n * g.GH + gy) * g.GW + gx) * g.ldg + g.g_coff + co);
+      }
+      *reinterpret_cast<float4*>(&Gs[kp][f4 * 4]) = v;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int kp = 0; kp < KP; ++kp) {
+      float a[TMW], gg[TNW];
+      load_frag<TMW>(&As[kp][0], tm, a);
+      load_frag<TNW>(&Gs[kp][0], tn, gg);
+#pragma unroll
+      for (int i = 0; i < TMW; ++i)
+#pragma unroll
+        for (int j = 0; j < TNW; ++j) acc[i][j] = fmaf(a[i], gg[j], acc[i][j]);
+      if (do_bias) {
+#pragma unroll
+        for (int j = 0; j < TNW; ++j) bsum[j] += gg[j];
+      }
+    }
+    __syncthreads();
+  }
+
+  float* slab = dW + (long)tc.widx[t] * s_t;
+#pragma unroll
+  for (int i = 0; i < TMW; ++i) {
+    const int ci = ci0 + frag_index<TMW>(tm, i);
+    if (ci >= g.CIN_VALID) continue;
+#pragma unroll
+    for (int j = 0; j < TNW; ++j) {
+      const int co = co0 + frag_index<TNW>(tn, j);
+      if (co < g.COUT) atomicAdd(slab + (long)ci * s_ci + (long)co * s_co, acc[i][j]);
+    }
+  }
+  if (do_bias) {
+#pragma unroll
+    for (int j = 0; j < TNW; ++j) {
+      const int co = co0 + frag_index<TNW>(tn, j);
+      if (co < g.COUT) atomicAdd(db + co, bsum[j]);
+    }
+  }
+}
+
+template <int TMW, int TNW, int KP>
+static int wgrad_launch(const ConvGeom& g, const float* A, const float* a_scale, const float* a_shift, const float* G,
+                        float* dW, long s_ci, long s_co, long s_t, float* db, cudaStream_t s) {
+  constexpr int CI_TILE = 16 * TMW, CO_TILE = 16 * TNW;
+  int total_taps = 0;
+  for (int c = 0; c < g.nclasses; ++c) total_taps += g.cls[c].ntaps;
+  int tiles = cdiv(g.CIN, CI_TILE) * cdiv(g.COUT, CO_TILE);
+  size_t P = (size_t)g.N * g.VH * g.VW;
+  int want = cdiv(2 * kNumSMs, total_taps * tiles);
+  if (want < 1) want = 1;
+  size_t ppc = (P + want - 1) / want;
+  ppc = (ppc + KP - 1) / KP * KP;
+  if (ppc < (size_t)KP) ppc = KP;
+  int ksplit = (int)((P + ppc - 1) / ppc);
+  dim3 grid((unsigned)ksplit, (unsigned)total_taps, (unsigned)tiles);
+  wgrad_taps_kernel<TMW, TNW, KP><<<grid, 256, 0, s>>>(g, A, a_scale, a_shift, G, dW, s_ci, s_co, s_t, db, (int)ppc);
+  MDIL_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_wgrad_taps(const ConvGeom& g, const float* A, const float* a_scale, const float* a_shift, const float* G,
+                      float* dW, long s_ci, long s_co, long s_t, float* db, cudaStream_t s) {
+  MDIL_REQUIRE(g.CIN % 4 == 0 && g.lda % 4 == 0 && g.a_coff % 4 == 0 && g.ldg % 4 == 0 && g.g_coff % 4 == 0,
+               "wgrad_taps: alignment");
+  const int tm = g.CIN >= 128 ? 8 : (g.CIN >= 64 ? 4 : 1);
+  const int tn = g.COUT >= 128 ? 8 : (g.COUT > 16 ? 4 : 1);
+#define MDIL_WG(TM_, TN_, KP_) \
+  if (tm == TM_ && tn == TN_) return wgrad_launch<TM_, TN_, KP_>(g, A, a_scale, a_shift, G, dW, s_ci, s_co, s_t, db, s)
+  MDIL_WG(8, 8, 16);
+  MDIL_WG(8, 4, 16);
+  MDIL_WG(8, 1, 16);
+  MDIL_WG(4, 8, 16);
+  MDIL_WG(4, 4, 16);
+  MDIL_WG(4, 1, 16);
+  MDIL_WG(1, 8, 16);
+  MDIL_WG(1, 4, 16);
+  MDIL_WG(1, 1, 64);
+#undef MDIL_WG
+  return set_error(-2, "wgrad_taps: no kernel for this shape", __FILE__, __LINE__);
+}
+
+// ============================================================================ weight packing
+__global__ void pack_kernel(const float* __restrict__ src, float* __restrict__ dst, int T, int A, int Apad, int B, int Bpad,
+                            long sa, long sb, long st, int flip) {
+  const long total = (long)T * Apad * Bpad;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int b = (int)(i % Bpad);
+    const long r = i / Bpad;
+    const int a = (int)(r % Apad);
+    const int td = (int)(r / Apad);
+    const int t = flip ? T - 1 - td : td;
+    dst[i] = (a < A && b < B) ? __ldg(src + a * sa + b * sb + t * st) : 0.f;
+  }
+}
+
+int launch_pack(const float* src, float* dst, int T, int A, int Apad, int B, int Bpad, long sa, long sb, long st, int flip,
+                cudaStream_t s) {
+  long total = (long)T * Apad * Bpad;
+  int grid = (int)((total + 255) / 256);
+  if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+  if (grid < 1) grid = 1;
+  pack_kernel<<<grid, 256, 0, s>>>(src, dst, T, A, Apad, B, Bpad, sa, sb, st, flip);
+  MDIL_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace mdil

@@ -1,0 +1,359 @@
+// Bandwidth-bound helper kernels: layout conversion, per-domain BatchNorm statistics / apply /
+// backward, max-pool branch of the DownsamplerBlock, scaling, Adam.
+// All activations NHWC fp32, 128-bit accesses along C, grids sized in multiples of the SM count.
+#include "kernels.cuh"
+
+namespace mdil {
+
+static inline int ew_grid(size_t work_items, int per_block) {
+  size_t need = (work_items + per_block - 1) / per_block;
+  size_t cap = (size_t)kNumSMs * 16;
+  if (need < 1) need = 1;
+  return (int)(need < cap ? need : cap);
+}
+
+// ------------------------------------------------------------------ NCHW -> NHWC4
+__global__ void nchw_to_nhwc4_kernel(const float* __restrict__ x, float* __restrict__ y, int C, size_t HW, size_t total) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    size_t n = i / HW, p = i % HW;
+    const float* src = x + n * C * HW + p;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    v.x = __ldg(src);
+    if (C > 1) v.y = __ldg(src + HW);
+    if (C > 2) v.z = __ldg(src + 2 * HW);
+    if (C > 3) v.w = __ldg(src + 3 * HW);
+    reinterpret_cast<float4*>(y)[i] = v;
+  }
+}
+
+int launch_nchw_to_nhwc4(const float* x, float* y, int N, int C, int H, int W, cudaStream_t s) {
+  MDIL_REQUIRE(C >= 1 && C <= 4, "nchw_to_nhwc4: C must be 1..4");
+  size_t HW = (size_t)H * W, total = (size_t)N * HW;
+  nchw_to_nhwc4_kernel<<<ew_grid(total, 256), 256, 0, s>>>(x, y, C, HW, total);
+  MDIL_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------ channel statistics
+// Thread layout: C4 = C/4 threads span the channels of one pixel (one float4 each), 256/C4 pixel lanes.
+// Per-thread fp32 partials over a short strided pixel walk, fp64 across lanes / CTAs.
+template <int MODE>  // 0: sum x, sum x^2 ; 1: bn-backward sums (dz, dz*uhat)
+__global__ void __launch_bounds__(256)
+stats_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ drop,
+             const float* __restrict__ u, const float* __restrict__ stats, size_t P, size_t HW, int C,
+             double* __restrict__ sums) {
+  extern __shared__ double sh[];  // [2][lanes][C]
+  const int C4 = C >> 2;
+  const int lanes = 256 / C4;
+  const int c4 = threadIdx.x % C4;
+  const int lane = threadIdx.x / C4;
+  float4 s1 = make4(0.f), s2 = make4(0.f);
+  float4 mean = make4(0.f), istd = make4(0.f);
+  if (MODE == 1) {
+    mean = ldg4(stats + c4 * 4);
+    istd = ldg4(stats + C + c4 * 4);
+  }
+  for (size_t p = (size_t)blockIdx.x * lanes + lane; p < P; p += (size_t)gridDim.x * lanes) {
+    float4 v = ldg4(x + p * C + c4 * 4);
+    if (MODE == 0) {
+      s1.x += v.x; s1.y += v.y; s1.z += v.z; s1.w += v.w;
+      s2.x += v.x * v.x; s2.y += v.y * v.y; s2.z += v.z * v.z; s2.w += v.w * v.w;
+    } else {
+      if (y != nullptr) {
+        float4 yy = ldg4(y + p * C + c4 * 4);
+        v.x = yy.x > 0.f ? v.x : 0.f; v.y = yy.y > 0.f ? v.y : 0.f;
+        v.z = yy.z > 0.f ? v.z : 0.f; v.w = yy.w > 0.f ? v.w : 0.f;
+      }
+      if (drop != nullptr) {
+        float4 d = ldg4(drop + (p / HW) * C + c4 * 4);
+        v.x *= d.x; v.y *= d.y; v.z *= d.z; v.w *= d.w;
+      }
+      float4 uu = ldg4(u + p * C + c4 * 4);
+      s1.x += v.x; s1.y += v.y; s1.z += v.z; s1.w += v.w;
+      s2.x += v.x * ((uu.x - mean.x) * istd.x); s2.y += v.y * ((uu.y - mean.y) * istd.y);
+      s2.z += v.z * ((uu.z - mean.z) * istd.z); s2.w += v.w * ((uu.w - mean.w) * istd.w);
+    }
+  }
+  double* a = sh + (size_t)lane * C + c4 * 4;
+  double* b = sh + (size_t)lanes * C + (size_t)lane * C + c4 * 4;
+  a[0] = s1.x; a[1] = s1.y; a[2] = s1.z; a[3] = s1.w;
+  b[0] = s2.x; b[1] = s2.y; b[2] = s2.z; b[3] = s2.w;
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * C; c += 256) {
+    int which = c / C, ch = c % C;
+    double t = 0.0;
+    for (int l = 0; l < lanes; ++l) t += sh[(size_t)which * lanes * C + (size_t)l * C + ch];
+    atomicAdd(sums + which * C + ch, t);
+  }
+}
+
+static int stats_grid(size_t P, int lanes) {
+  size_t need = (P + lanes - 1) / lanes;
+  size_t cap = (size_t)kNumSMs * 4;
+  if (need < 1) need = 1;
+  return (int)(need < cap ? need : cap);
+}
+
+int launch_channel_stats(const float* x, size_t P, int ld, int coff, int cnt, double* sums, int ldsum, cudaStream_t s) {
+  MDIL_REQUIRE(coff == 0 && ld == cnt && ldsum == cnt, "channel_stats: only full-width tensors supported");
+  int C = cnt;
+  MDIL_REQUIRE(C % 4 == 0 && 256 % (C / 4) == 0, "channel_stats: unsupported channel count");
+  int lanes = 256 / (C / 4);
+  size_t smem = (size_t)2 * lanes * C * sizeof(double);
+  stats_kernel<0><<<stats_grid(P, lanes), 256, smem, s>>>(x, nullptr, nullptr, nullptr, nullptr, P, 1, C, sums);
+  MDIL_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_bn_bwd_stats(const float* dy, const float* y, const float* drop, const float* u, const float* stats,
+                        double* sums, int N, size_t HW, int C, cudaStream_t s) {
+  MDIL_REQUIRE(C % 4 == 0 && 256 % (C / 4) == 0, "bn_bwd_stats: unsupported channel count");
+  int lanes = 256 / (C / 4);
+  size_t P = (size_t)N * HW;
+  size_t smem = (size_t)2 * lanes * C * sizeof(double);
+  stats_kernel<1><<<stats_grid(P, lanes), 256, smem, s>>>(dy, y, drop, u, stats, P, HW, C, sums);
+  MDIL_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------ BN finalize (forward)
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, int ldsum, double count, int C,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float* rm, float* rv,
+                                   float eps, float momentum, int train, float* __restrict__ stats) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float mean, var;
+  if (train) {
+    double m = sums[c] / count;
+    double v = sums[ldsum + c] / count - m * m;
+    if (v < 0.0) v = 0.0;
+    mean = (float)m;
+    var = (float)v;
+    double unbiased = count > 1.0 ? v * count / (count - 1.0) : v;
+    rm[c] = (1.f - momentum) * rm[c] + momentum * mean;
+    rv[c] = (1.f - momentum) * rv[c] + momentum * (float)unbiased;
+  } else {
+    mean = rm[c];
+    var = rv[c];
+  }
+  float invstd = 1.0f / sqrtf(var + eps);
+  float scale = gamma[c] * invstd;
+  stats[c] = mean;
+  stats[C + c] = invstd;
+  stats[2 * C + c] = scale;
+  stats[3 * C + c] = beta[c] - mean * scale;
+}
+
+int launch_bn_finalize(const double* sums, int ldsum, double count, int C, const float* gamma, const float* beta,
+                       float* rm, float* rv, float eps, float momentum, int train, float* stats, cudaStream_t s) {
+  bn_finalize_kernel<<<cdiv(C, 128), 128, 0, s>>>(sums, ldsum, count, C, gamma, beta, rm, rv, eps, momentum, train, stats);
+  MDIL_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------ BN apply + dropout + residual + ReLU
+__global__ void __launch_bounds__(256)
+bn_act_kernel(const float* __restrict__ u, const float* __restrict__ stats, const float* __restrict__ drop,
+              const float* __restrict__ res, float* __restrict__ y, size_t total4, size_t HWC4, int C) {
+  const int C4 = C >> 2;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
+    int c4 = (int)(i % C4);
+    float4 v = ldg4(u + i * 4);
+    float4 sc = ldg4(stats + 2 * C + c4 * 4), sh = ldg4(stats + 3 * C + c4 * 4);
+    v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+    if (drop != nullptr) {
+      float4 d = ldg4(drop + (i / HWC4) * C + c4 * 4);
+      v.x *= d.x; v.y *= d.y; v.z *= d.z; v.w *= d.w;
+    }
+    if (res != nullptr) {
+      float4 r = ldg4(res + i * 4);
+      v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+    }
+    v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+    reinterpret_cast<float4*>(y)[i] = v;
+  }
+}
+
+int launch_bn_act(const float* u, const float* stats, const float* drop, const float* res, float* y, int N, size_t HW,
+                  int C, cudaStream_t s) {
+  MDIL_REQUIRE(C % 4 == 0, "bn_act: C % 4");
+  size_t total4 = (size_t)N * HW * (C / 4);
+  bn_act_kernel<<<ew_grid(total4, 256), 256, 0, s>>>(u, stats, drop, res, y, total4, HW * (C / 4), C);
+  MDIL_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------ BN backward finalize / apply
+__global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, double count, int C,
+                                       const float* __restrict__ gamma, const float* __restrict__ stats,
+                                       float* __restrict__ coef, float* dgamma, float* dbeta) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double sdz = sums[c], sdzu = sums[C + c];
+  coef[c] = gamma[c] * stats[C + c];
+  coef[C + c] = (float)(sdz / count);
+  coef[2 * C + c] = (float)(sdzu / count);
+  if (dgamma != nullptr) dgamma[c] = (float)sdzu;
+  if (dbeta != nullptr) dbeta[c] = (float)sdz;
+}
+
+int launch_bn_bwd_finalize(const double* sums, double count, int C, const float* gamma, const float* stats, float* coef,
+                           float* dgamma, float* dbeta, cudaStream_t s) {
+  bn_bwd_finalize_kernel<<<cdiv(C, 128), 128, 0, s>>>(sums, count, C, gamma, stats, coef, dgamma, dbeta);
+  MDIL_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ drop,
+                    const float* __restrict__ u, const float* __restrict__ stats, const float* __restrict__ coef,
+                    float* __restrict__ du, size_t total4, size_t HWC4, int C) {
+  const int C4 = C >> 2;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
+    int c4 = (int)(i % C4);
+    float4 v = ldg4(dy + i * 4);
+    if (y != nullptr) {
+      float4 yy = ldg4(y + i * 4);
+      v.x = yy.x > 0.f ? v.x : 0.f; v.y = yy.y > 0.f ? v.y : 0.f;
+      v.z = yy.z > 0.f ? v.z : 0.f; v.w = yy.w > 0.f ? v.w : 0.f;
+    }
+    if (drop != nullptr) {
+      float4 d = ldg4(drop + (i / HWC4) * C + c4 * 4);
+      v.x *= d.x; v.y *= d.y; v.z *= d.z; v.w *= d.w;
+    }
+    float4 uu = ldg4(u + i * 4);
+    float4 mean = ldg4(stats + c4 * 4), istd = ldg4(stats + C + c4 * 4);
+    float4 g = ldg4(coef + c4 * 4), k1 = ldg4(coef + C + c4 * 4), k2 = ldg4(coef + 2 * C + c4 * 4);
+    float4 o;
+    o.x = g.x * (v.x - k1.x - (uu.x - mean.x) * istd.x * k2.x);
+    o.y = g.y * (v.y - k1.y - (uu.y - mean.y) * istd.y * k2.y);
+    o.z = g.z * (v.z - k1.z - (uu.z - mean.z) * istd.z * k2.z);
+    o.w = g.w * (v.w - k1.w - (uu.w - mean.w) * istd.w * k2.w);
+    reinterpret_cast<float4*>(du)[i] = o;
+  }
+}
+
+int launch_bn_bwd_apply(const float* dy, const float* y, const float* drop, const float* u, const float* stats,
+                        const float* coef, float* du, int N, size_t HW, int C, cudaStream_t s) {
+  MDIL_REQUIRE(C % 4 == 0, "bn_bwd_apply: C % 4");
+  size_t total4 = (size_t)N * HW * (C / 4);
+  bn_bwd_apply_kernel<<<ew_grid(total4, 256), 256, 0, s>>>(dy, y, drop, u, stats, coef, du, total4, HW * (C / 4), C);
+  MDIL_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------ max-pool branch
+__global__ void __launch_bounds__(256)
+pool_fwd_kernel(const float* __restrict__ x, float* __restrict__ u, int H, int W, int Cin, int ldin, int ldu, int coff,
+                size_t total) {
+  const int OH = H >> 1, OW = W >> 1;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % Cin);
+    size_t p = i / Cin;
+    int ox = (int)(p % OW);
+    size_t t = p / OW;
+    int oy = (int)(t % OH);
+    size_t n = t / OH;
+    const float* b = x + ((n * H + 2 * oy) * (size_t)W + 2 * ox) * ldin + c;
+    float m = __ldg(b);
+    m = fmaxf(m, __ldg(b + ldin));
+    m = fmaxf(m, __ldg(b + (size_t)W * ldin));
+    m = fmaxf(m, __ldg(b + (size_t)W * ldin + ldin));
+    u[p * ldu + coff + c] = m;
+  }
+}
+
+int launch_pool_fwd(const float* x, float* u, int N, int H, int W, int Cin, int ldin, int ldu, int coff, cudaStream_t s) {
+  size_t total = (size_t)N * (H / 2) * (W / 2) * Cin;
+  pool_fwd_kernel<<<ew_grid(total, 256), 256, 0, s>>>(x, u, H, W, Cin, ldin, ldu, coff, total);
+  MDIL_LAUNCH_CHECK();
+  return 0;
+}
+
+// First maximum in row-major window order wins (torch max_pool2d backward).
+__global__ void __launch_bounds__(256)
+pool_bwd_kernel(const float* __restrict__ x, const float* __restrict__ du, float* __restrict__ dx, int H, int W, int Cin,
+                int ldin, int ldu, int coff, int accumulate, size_t total) {
+  const int OH = H >> 1, OW = W >> 1;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % Cin);
+    size_t p = i / Cin;
+    int ox = (int)(p % OW);
+    size_t t = p / OW;
+    int oy = (int)(t % OH);
+    size_t n = t / OH;
+    size_t base = ((n * H + 2 * oy) * (size_t)W + 2 * ox);
+    const float* b = x + base * ldin + c;
+    float v0 = __ldg(b), v1 = __ldg(b + ldin), v2 = __ldg(b + (size_t)W * ldin), v3 = __ldg(b + (size_t)W * ldin + ldin);
+    int arg = 0;
+    float m = v0;
+    if (v1 > m) { m = v1; arg = 1; }
+    if (v2 > m) { m = v2; arg = 2; }
+    if (v3 > m) { m = v3; arg = 3; }
+    float g = __ldg(du + p * ldu + coff + c);
+    float* d = dx + base * Cin + c;
+    size_t offs[4] = {0, (size_t)Cin, (size_t)W * Cin, (size_t)W * Cin + Cin};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float val = (k == arg) ? g : 0.f;
+      if (accumulate) d[offs[k]] += val; else d[offs[k]] = val;
+    }
+  }
+}
+
+int launch_pool_bwd(const float* x, const float* du, float* dx, int N, int H, int W, int Cin, int ldin, int ldu,
+                    int coff, int accumulate, cudaStream_t s) {
+  size_t total = (size_t)N * (H / 2) * (W / 2) * Cin;
+  pool_bwd_kernel<<<ew_grid(total, 256), 256, 0, s>>>(x, du, dx, H, W, Cin, ldin, ldu, coff, accumulate, total);
+  MDIL_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------ scaling / Adam
+__global__ void __launch_bounds__(256)
+scale_kernel(float* __restrict__ x, size_t n4, size_t n, const double* __restrict__ den, const float* __restrict__ mul) {
+  float f = 1.0f;
+  if (mul != nullptr) f *= __ldg(mul);
+  if (den != nullptr) f = (float)((double)f / den[0]);
+  if (f == 1.0f) return;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 v = reinterpret_cast<float4*>(x)[i];
+    v.x *= f; v.y *= f; v.z *= f; v.w *= f;
+    reinterpret_cast<float4*>(x)[i] = v;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) x[n4 * 4 + threadIdx.x] *= f;
+}
+
+int launch_scale(float* x, size_t n, const double* den, const float* mul, cudaStream_t s) {
+  MDIL_REQUIRE(((uintptr_t)x & 15) == 0, "scale: pointer must be 16-byte aligned");
+  size_t n4 = n / 4;
+  scale_kernel<<<ew_grid(n4, 256), 256, 0, s>>>(x, n4, n, den, mul);
+  MDIL_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, size_t n,
+            float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt, float grad_scale) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float pi = p[i];
+    float gi = g[i] * grad_scale + wd * pi;
+    float mi = b1 * m[i] + (1.f - b1) * gi;
+    float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - (lr / bc1) * (mi / denom);
+  }
+}
+
+int launch_adam(float* param, const float* grad, float* m, float* v, size_t n, float lr, float b1, float b2, float eps,
+                float wd, int step, float grad_scale, cudaStream_t s) {
+  float bc1 = 1.f - powf(b1, (float)step);
+  float bc2 = 1.f - powf(b2, (float)step);
+  adam_kernel<<<ew_grid(n, 256), 256, 0, s>>>(param, grad, m, v, n, lr, b1, b2, eps, wd, bc1, sqrtf(bc2), grad_scale);
+  MDIL_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace mdil

@@ -1,0 +1,117 @@
+// Internal launcher interface between api.cu (C ABI, orchestration) and the kernel files.
+#pragma once
+#include "common.cuh"
+
+namespace mdil {
+
+// ---------------------------------------------------------------- elementwise.cu
+int launch_nchw_to_nhwc4(const float* x, float* y, int N, int C, int H, int W, cudaStream_t s);
+
+// sums[0*ldsum + coff + c] += sum x, sums[1*ldsum + coff + c] += sum x^2 over P pixels, channels [coff, coff+cnt)
+int launch_channel_stats(const float* x, size_t P, int ld, int coff, int cnt, double* sums, int ldsum, cudaStream_t s);
+
+// stats [4][C] = mean, invstd, scale (=gamma*invstd), shift (=beta-mean*scale).
+// train: batch statistics from sums (count pixels) and running-stat update; else running stats.
+int launch_bn_finalize(const double* sums, int ldsum, double count, int C, const float* gamma, const float* beta,
+                       float* running_mean, float* running_var, float eps, float momentum, int train, float* stats,
+                       cudaStream_t s);
+
+// y = relu((u*scale+shift) * drop[n][c] + res)   (drop, res nullable)
+int launch_bn_act(const float* u, const float* stats, const float* drop, const float* res, float* y, int N, size_t HW,
+                  int C, cudaStream_t s);
+
+// dz = dy * (y>0) * drop ; sums[0][c] += sum dz ; sums[1][c] += sum dz*uhat, uhat = (u-mean)*invstd
+// (y, drop nullable: dz = dy)
+int launch_bn_bwd_stats(const float* dy, const float* y, const float* drop, const float* u, const float* stats,
+                        double* sums, int N, size_t HW, int C, cudaStream_t s);
+
+// coef [3][C] = gamma*invstd, sum dz / n, sum dz*uhat / n ; dgamma/dbeta nullable
+int launch_bn_bwd_finalize(const double* sums, double count, int C, const float* gamma, const float* stats, float* coef,
+                           float* dgamma, float* dbeta, cudaStream_t s);
+
+// du = coef0 * (dz - coef1 - uhat*coef2)
+int launch_bn_bwd_apply(const float* dy, const float* y, const float* drop, const float* u, const float* stats,
+                        const float* coef, float* du, int N, size_t HW, int C, cudaStream_t s);
+
+// max-pool 2x2 s2 of x[N,H,W,ldin] channels [0,Cin) -> u[N,H/2,W/2,ldu] channels [coff, coff+Cin)
+int launch_pool_fwd(const float* x, float* u, int N, int H, int W, int Cin, int ldin, int ldu, int coff, cudaStream_t s);
+// dx[N,H,W,Cin] (+)= du routed to the first max of each window; accumulate != 0 adds to dx
+int launch_pool_bwd(const float* x, const float* du, float* dx, int N, int H, int W, int Cin, int ldin, int ldu,
+                    int coff, int accumulate, cudaStream_t s);
+
+int launch_scale(float* x, size_t n, const double* inv_den /*nullable: multiply by 1/(*inv_den)*/, const float* mul,
+                 cudaStream_t s);
+int launch_adam(float* param, const float* grad, float* m, float* v, size_t n, float lr, float b1, float b2, float eps,
+                float wd, int step, float grad_scale, cudaStream_t s);
+
+// ---------------------------------------------------------------- conv_taps.cu
+constexpr int kMaxTaps = 9;
+constexpr int kMaxClasses = 4;
+
+struct TapClass {
+  int ntaps;
+  int o_dy, o_dx;  // forward: output coordinate offset of this class
+  int a_dy[kMaxTaps], a_dx[kMaxTaps];
+  int widx[kMaxTaps];                  // which [CIN][COUT] weight slab
+};
+
+// Virtual grid (n, vy, vx). A coordinate = v*a_s + a_d[t]; G coordinate = v*g_s + o_d(class).
+struct ConvGeom {
+  int N, VH, VW;
+  int AH, AW, lda, a_coff, a_sy, a_sx;
+  int GH, GW, ldg, g_coff, g_sy, g_sx;
+  int CIN, COUT, COUT_PAD;
+  int CIN_VALID;  // wgrad: rows ci >= CIN_VALID are padding and not written
+  int nclasses;
+  TapClass cls[kMaxClasses];
+};
+
+// out[g pixel][g_coff+co] = bias[co] + sum_t sum_ci A[a pixel(t)][a_coff+ci] * Wp[widx[t]][ci][co]
+int launch_conv_taps(const ConvGeom& g, const float* A, const float* Wp, const float* bias, float* out,
+                     cudaStream_t s);
+
+// dW[ci*s_ci + co*s_co + widx*s_t] += sum_pixels A'[a pixel(t)][ci] * G[g pixel][co]   (dW, db zeroed by the caller)
+// A' = relu(A*a_scale+a_shift) when a_scale != NULL.  db[co] += sum of G over the tap-0 walk of every class.
+int launch_wgrad_taps(const ConvGeom& g, const float* A, const float* a_scale, const float* a_shift, const float* G,
+                      float* dW, long s_ci, long s_co, long s_t, float* db, cudaStream_t s);
+
+// dst[(tmap(t)*Apad + a)*Bpad + b] = src[a*sa + b*sb + t*st] for a<A, b<B, else 0; flip: tmap(t)=T-1-t
+int launch_pack(const float* src, float* dst, int T, int A, int Apad, int B, int Bpad, long sa, long sb, long st, int flip,
+                cudaStream_t s);
+
+// ---------------------------------------------------------------- nb1d_pair.cu
+enum PairEpilogue { kEpiFwd = 0, kEpiBwdMaskStats = 1, kEpiBwdResidual = 2 };
+
+struct PairArgs {
+  const float* in;         // [N,H,W,C]
+  const float* in_scale;   // nullable: prologue v = relu(v*scale+shift)
+  const float* in_shift;
+  const float* wstream;    // packed [3][C][C] first conv, [3][C][C] second conv, [C][C] adapter (if has_adapter)
+  const float* b1;         // nullable
+  const float* b2;         // nullable
+  const float* bad;        // nullable (adapter bias)
+  const float* mid_mask;   // nullable: mid = acc * (mid_mask > 0) instead of relu(acc + b1)
+  float* mid_out;          // nullable: store mid (a / c / dc' / da')
+  float* out;
+  int epi;
+  const float* e0;         // epi1: p            epi2: dy
+  const float* e1;         // epi2: y
+  const float* e_stats;    // epi1: [4][C] mean, invstd, scale, shift of BN1
+  double* sums;            // nullable: [2][C] (fwd: sum out, sum out^2; epi1: sum out, sum out*phat)
+  int N, H, W, C, dil, has_adapter, vert_first;
+};
+int launch_pair(const PairArgs& a, cudaStream_t s);
+
+// ---------------------------------------------------------------- head_loss.cu
+int launch_outconv_fwd(const float* x, const float* w, const float* bias, float* logits, int N, int H, int W, int Ccls,
+                       cudaStream_t s);
+int launch_outconv_bwd(const float* dlogits, const float* x, const float* w, float* dx, float* dw, float* db, int N,
+                       int H, int W, int Ccls, cudaStream_t s);
+int launch_ce2d(const float* logits, const int64_t* labels, const float* class_w, int N, int C, int H, int W,
+                float* loss, double* acc, float* dlogits, cudaStream_t s);
+int launch_kd(const float* student, const float* teacher, int N, int C, int H, int W, float* loss, double* acc,
+              float* dstudent, cudaStream_t s);
+int launch_argmax_confusion(const float* logits, const int64_t* labels, int N, int C, int H, int W, int64_t* pred,
+                            long long* conf, cudaStream_t s);
+
+}  // namespace mdil

@@ -242,7 +242,7 @@ def trainable_names_incremental(sd: SD, current_task: int) -> List[str]:
             if f"decoder.{current_task}" in n:
                 out.append(n)
         elif "encoder" in n and ("bn" in n or "parallel_conv" in n):
-            if f".{current_task}." in n:
+            if f".{current_task}.weight" in n or f".{current_task}.bias" in n:
                 out.append(n)
         else:
             out.append(n)

@@ -1,0 +1,52 @@
+"""Shared helpers of the test-suite (test infrastructure: may import oracle/)."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+REPO = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+GOLDEN = os.path.join(REPO, "tests", "golden")
+REFERENCE = os.environ.get("MDIL_REFERENCE", "/root/reference")
+
+from oracle import erfnet_rap_oracle as oracle  # noqa: E402
+
+
+def golden(name):
+    return np.load(os.path.join(GOLDEN, name), allow_pickle=False)
+
+
+def make_sd(classes, init_seed, bn_seed):
+    """The state_dict the fixtures were generated with: reference-order default init under `init_seed`
+    (oracle.init_state_dict restates the constructors) + deterministic non-trivial BatchNorm state."""
+    sd = oracle.init_state_dict(classes, len(classes), seed=init_seed)
+    return oracle.perturb_bn_(sd, seed=bn_seed)
+
+
+def noise_list(npz, prefix, n_layers=15):
+    out = []
+    for i in range(n_layers):
+        k = f"{prefix}{i}"
+        out.append(torch.from_numpy(npz[k]) if k in npz.files else None)
+    return out
+
+
+def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    denom = b.abs().max().item()
+    return (a - b).abs().max().item() / (denom if denom > 0 else 1.0)
+
+
+def assert_close(a, b, tol, what="", atol=0.0):
+    """max|a-b| <= tol * max|b| + atol (max-norm relative error; atol covers mathematically-zero tensors such as
+    the gradient of a conv bias feeding a train-mode BatchNorm)."""
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    assert a.shape == b.shape, f"{what}: shape {tuple(a.shape)} vs {tuple(b.shape)}"
+    err = (a - b).abs().max().item() if a.numel() else 0.0
+    ref = b.abs().max().item() if b.numel() else 0.0
+    assert err <= tol * ref + atol, f"{what}: max abs error {err:.3e} (ref max {ref:.3e}) exceeds {tol:.1e} relative + {atol:.1e}"
+    return err / ref if ref > 0 else err

@@ -1,0 +1,112 @@
+"""CPU: pin oracle/erfnet_rap_oracle.py against the fixtures produced by the unmodified reference
+(tests/golden/make_golden.py).  The reference has no tests of its own, so these
+reference-generated vectors are the pin."""
+import json
+import os
+
+import numpy as np
+import torch
+
+from _util import GOLDEN, assert_close, golden, make_sd, noise_list, oracle
+
+TOL = 2e-5  # same ATen CPU kernels on both sides; only thread-count dependent summation order differs
+
+
+def test_constructor_contract():
+    contract = json.load(open(os.path.join(GOLDEN, "contract.json")))
+    for classes in ([20], [20, 20], [20, 20, 27]):
+        c = contract[str(len(classes))]
+        sd = oracle.init_state_dict(classes, len(classes), seed=0)
+        assert list(sd.keys()) == c["keys"]
+        assert [list(v.shape) for v in sd.values()] == c["shapes"]
+        assert oracle.param_names(sd) == c["params"]
+        cs = float(sum(v.double().sum() for v in sd.values() if v.dtype.is_floating_point))
+        assert abs(cs - c["checksum"]) <= 1e-9 * max(1.0, abs(c["checksum"]))
+    assert len(contract["1"]["keys"]) == 395 and len(contract["2"]["keys"]) == 680 and len(contract["3"]["keys"]) == 965
+
+
+def test_eval_forward_fixtures():
+    for name in ("eval_1task.npz", "eval_3task_t2.npz", "eval_3task_t0.npz"):
+        g = golden(name)
+        classes = [int(c) for c in g["classes"]]
+        sd = make_sd(classes, int(g["seed"]), int(g["bn_seed"]))
+        x = torch.rand(1, 3, 64, 128, generator=torch.Generator().manual_seed(int(g["x_seed"])))
+        with torch.no_grad():
+            y = oracle.net_forward(sd, x, int(g["task"]), False)
+        ref = torch.from_numpy(g["logits"])
+        assert y.shape == ref.shape
+        assert_close(y, ref, TOL, name)
+        assert torch.equal(y.argmax(1), ref.argmax(1))
+
+
+def _train_inputs(g):
+    gen = torch.Generator().manual_seed(int(g["x_seed"]))
+    x = torch.rand(2, 3, 32, 64, generator=gen)
+    labels = torch.randint(0, 20, (2, 1, 32, 64), generator=gen)
+    return x, labels
+
+
+def test_train_forward_backward_fixture():
+    g = golden("train_2task_t1.npz")
+    sd = make_sd([20, 20], int(g["init_seed"]), int(g["bn_seed"]))
+    x, labels = _train_inputs(g)
+    noise = noise_list(g, "noise_")
+    torch.manual_seed(int(g["noise_seed"]))
+    regenerated = oracle.make_dropout_noise(2, True)
+    for a, b in zip(noise, regenerated):
+        assert (a is None) == (b is None)
+        if a is not None:
+            assert torch.equal(a, b)
+    names = oracle.param_names(sd)
+    work = dict(sd)
+    for n in names:
+        work[n] = sd[n].detach().requires_grad_(True)
+    logits = oracle.net_forward(work, x, 1, True, noise)
+    loss = oracle.cross_entropy2d(logits, labels[:, 0], torch.tensor(oracle.WEIGHT_BDD))
+    grads = torch.autograd.grad(loss, [work[n] for n in names], allow_unused=True)
+    gd = {n: gr for n, gr in zip(names, grads) if gr is not None}
+    assert_close(logits, torch.from_numpy(g["logits"]), TOL, "logits")
+    assert abs(float(loss) - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    assert list(gd.keys()) == [str(s) for s in g["grad_names"]]
+    gabs = np.array([float(v.double().abs().sum()) for v in gd.values()])
+    np.testing.assert_allclose(gabs, g["grad_abs"], rtol=2e-4, atol=2e-5)
+    for i, n in enumerate([str(s) for s in g["pick"]]):
+        assert_close(gd[n], torch.from_numpy(g[f"grad_{i}"]), 2e-4, n, atol=1e-6)
+    bn_sum = np.array([float(sd[str(k)].double().sum()) for k in g["bn_names"]])
+    np.testing.assert_allclose(bn_sum, g["bn_sum"], rtol=1e-5, atol=1e-6)
+
+
+def test_loss_fixtures():
+    g = golden("losses.npz")
+    for c, wts in ((20, oracle.WEIGHT_CITY), (27, oracle.WEIGHT_IDD)):
+        lg = torch.from_numpy(g[f"lg{c}"]).requires_grad_(True)
+        loss = oracle.cross_entropy2d(lg, torch.from_numpy(g[f"lb{c}"]), torch.tensor(wts))
+        loss.backward()
+        assert abs(float(loss) - float(g[f"ce{c}"])) <= 1e-6 * abs(float(g[f"ce{c}"]))
+        assert_close(lg.grad, torch.from_numpy(g[f"dlg{c}"]), 1e-5, f"dlogits{c}")
+    st = torch.from_numpy(g["st"]).requires_grad_(True)
+    kd = oracle.kd_loss(st, torch.from_numpy(g["te"]))
+    kd.backward()
+    assert abs(float(kd) - float(g["kd"])) <= 1e-6 * abs(float(g["kd"]))
+    assert float(kd) < 0  # the reference's KD value is negative by construction (probabilities as the input)
+    assert_close(st.grad, torch.from_numpy(g["dst"]), 1e-5, "dstudent")
+
+
+def test_step2_iteration_fixture():
+    g = golden("step2_iter.npz")
+    sd_old = make_sd([20], 9, 13)
+    sd = make_sd([20, 20], 10, 14)
+    gen = torch.Generator().manual_seed(400)
+    x = torch.rand(2, 3, 32, 64, generator=gen)
+    labels = torch.randint(0, 20, (2, 1, 32, 64), generator=gen)
+    ce, kd, out_t, gdict = oracle.step2_iteration(sd, sd_old, x, labels, torch.tensor(oracle.WEIGHT_BDD), 1, 0.1,
+                                                  noise_list(g, "noise_t_"), noise_list(g, "noise_prev_"))
+    assert abs(float(ce) - float(g["ce"])) <= 1e-5 * abs(float(g["ce"]))
+    assert abs(float(kd) - float(g["kd"])) <= 1e-5 * abs(float(g["kd"]))
+    assert_close(out_t, torch.from_numpy(g["out_t"]), TOL, "out_t")
+    names = [str(s) for s in g["grad_names"]]
+    assert sorted(names) == sorted(gdict.keys())
+    gabs = np.array([float(gdict[n].double().abs().sum()) for n in names])
+    np.testing.assert_allclose(gabs, g["grad_abs"], rtol=5e-4, atol=2e-5)
+    after = np.array([float(sd[str(k)].double().sum()) for k in g["after_names"]])
+    np.testing.assert_allclose(after, g["after_sum"], rtol=1e-5, atol=2e-4)

@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""bench.py — 512x1024 training crops/sec of the MDIL-SS hot path on N B200s (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload step1|step2]
+
+A "step" is one pass of the hot path over one batch of synthetic Cityscapes-shaped input:
+  step1 (default, BASELINE configs[1]): Step-1 single-domain train, 20 classes, batch 6 per GPU, 512x1024:
+        forward (train BN, dropout) -> CrossEntropy2d -> backward -> [one gradient all-reduce] -> Adam.
+  step2 (configs[2] shape per GPU): 2-domain adapters + KD: student fwd x2, teacher fwd, CE + 0.1*KD, backward, Adam.
+Per-GPU work is fixed as N grows (weak scaling); value = crops all ranks processed / max-over-ranks device time.
+`--impl reference` times the reference algorithm's CPU implementation (the oracle port: the reference is pure
+Python/PyTorch and /root/reference does not exist on the GPU box) on a bounded sample, all host threads.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+H, W, NCLS, BATCH_PER_GPU = 512, 1024, 20, 6
+METRIC = "train_crops_per_sec_512x1024"
+UNIT = "crops/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="step1", choices=["step1", "step2"])
+    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="crops per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(args):
+    if args.workload == "step1":
+        return (f"Step-1 CS single-domain train (fwd+CE2d+bwd+allreduce+Adam), 20 cls, batch {args.batch}/GPU, "
+                f"{H}x{W} synthetic")
+    return (f"Step-2 CS->BDD train (student fwd x2 + teacher fwd, CE2d + 0.1*KD, bwd, allreduce, Adam), 20/20 cls, "
+            f"batch {args.batch}/GPU, {H}x{W} synthetic")
+
+
+# ------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active") and not v.lower().startswith("not"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------- CPU arm
+def oracle_step_factory(workload, n):
+    import torch
+    from oracle import erfnet_rap_oracle as oracle
+    g = torch.Generator().manual_seed(1234)
+    images = torch.rand(n, 3, H, W, generator=g)
+    labels = torch.randint(0, NCLS, (n, 1, H // 32, W // 32), generator=g).repeat_interleave(32, 2).repeat_interleave(32, 3)
+    weight = torch.tensor(oracle.WEIGHT_CITY if workload == "step1" else oracle.WEIGHT_BDD)
+    if workload == "step1":
+        sd = oracle.init_state_dict([NCLS], 1, seed=0)
+        state = [dict() for _ in oracle.param_names(sd)]
+
+        def step():
+            torch.manual_seed(7)
+            noise = oracle.make_dropout_noise(n, True)
+            loss, _, _ = oracle.step1_iteration(sd, images, labels, weight, 0, noise, state)
+            return float(loss)
+    else:
+        sd_old = oracle.init_state_dict([NCLS], 1, seed=0)
+        sd = oracle.init_state_dict([NCLS, NCLS], 2, seed=1)
+        names = oracle.trainable_names_incremental(sd, 1)
+        state = [dict() for _ in names]
+
+        def step():
+            torch.manual_seed(7)
+            n1 = oracle.make_dropout_noise(n, True)
+            n2 = oracle.make_dropout_noise(n, True)
+            ce, kd, _, _ = oracle.step2_iteration(sd, sd_old, images, labels, weight, 1, 0.1, n1, n2, state)
+            return float(ce) + 0.1 * float(kd)
+    return step
+
+
+def time_cpu(workload, n, steps, warmup):
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step = oracle_step_factory(workload, n)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return n * steps / dt, dt / steps * 1e3, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = 1
+    steps = max(1, min(args.steps, 4))
+    warmup = 1
+    value, ms, cores = time_cpu(args.workload, n, steps, warmup)
+    sample = f"{steps} timed + {warmup} warm-up iterations of the same step at batch {n} (per-crop CPU cost is flat in N)"
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args), "arm": "reference algorithm on host CPU (oracle port, PyTorch ATen/oneDNN, fp32)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import ctypes
+    import torch
+    import torch.distributed as dist
+    from mdil_ss_b200 import _lib
+    from mdil_ss_b200.erfnet_RA_parallel import Net
+    from mdil_ss_b200.parallel import broadcast_module
+    from mdil_ss_b200.train_step import Step1Trainer, Step2Trainer, class_weights
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.lib()
+    if lib.mdil_device_supported(local_rank) != 1:
+        raise SystemExit("bench.py: libmdil_b200.so targets sm_100a (B200) only")
+
+    n = args.batch
+    torch.manual_seed(0)
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        if args.workload == "step1":
+            model = Net([NCLS], 1, 0).to(dev)
+        else:
+            model_old = Net([NCLS], 1, 0).to(dev)
+            model = Net([NCLS, NCLS], 2, 1).to(dev)
+    broadcast_module(model)
+    if args.workload == "step1":
+        trainer = Step1Trainer(model, class_weights("cityscapes", dev))
+    else:
+        broadcast_module(model_old)
+        trainer = Step2Trainer(model, model_old, class_weights("BDD", dev), 1, 0.1)
+
+    g = torch.Generator().manual_seed(1234 + rank)
+    images_h = torch.rand(n, 3, H, W, generator=g).pin_memory()
+    labels_h = (torch.randint(0, NCLS, (n, 1, H // 32, W // 32), generator=g)
+                .repeat_interleave(32, 2).repeat_interleave(32, 3).contiguous().pin_memory())
+    images = images_h.to(dev, non_blocking=True)
+    labels = labels_h.to(dev, non_blocking=True)
+
+    def step_resident():
+        return trainer.step(images, labels)
+
+    def step_e2e():
+        x = images_h.to(dev, non_blocking=True)
+        y = labels_h.to(dev, non_blocking=True)
+        out = trainer.step(x, y)
+        loss = out[0] if isinstance(out, tuple) else out
+        return float(loss)  # device -> host read of the step's result
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    for _ in range(max(3, args.warmup)):
+        step_resident()
+    # ---- timed region (device-resident inputs), clocks sampled during it, pair-kernel launches bracketed by events
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launches()
+    lib.mdil_profile_begin()
+    ms_total = timed(step_resident, args.steps)
+    nk = 12
+    tot = (ctypes.c_float * nk)()
+    cnt = (ctypes.c_int * nk)()
+    lib.mdil_profile_end(tot, cnt, nk)
+    launches = _lib.launches() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * n * args.steps / (ms_total / 1e3)
+
+    # ---- end-to-end: host buffers, H2D of the inputs and D2H of the loss inside the timed region
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    e2e_value = world * n * args.steps / (ms_e2e / 1e3)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak, peak_src = (peaks.get("hbm_gbs"), "measured (MEASURED_PEAKS.json hbm_gbs)") if peaks.get("hbm_gbs") \
+            else (6650.0, "fallback (B200_PROFILING.md)")
+        # dominant fused-block kernel: the kind with the largest total time
+        names = [f"nb1d_pair<C={c}> {ph}" for c in (16, 64, 128) for ph in ("fwd pair1", "fwd pair2", "bwd pair2", "bwd pair1")]
+        kind = max(range(nk), key=lambda i: tot[i])
+        c = (16, 64, 128)[kind // 4]
+        hh, ww = {16: (H // 2, W // 2), 64: (H // 4, W // 4), 128: (H // 8, W // 8)}[c]
+        T = 4.0 * n * c * hh * ww
+        alg_bytes = 2.0 * T  # read the pair's input tensor once, write its output tensor once
+        avg_ms = tot[kind] / max(1, cnt[kind])
+        achieved = alg_bytes / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+        pair_share = sum(tot) / ms_total if ms_total > 0 else 0.0
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                    "traffic": None, "kernel": names[kind], "avg_launch_ms": avg_ms, "launches_timed": int(cnt[kind]),
+                    "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                    "pair_kernels_share_of_step": pair_share,
+                    "per_kind_ms_per_step": {names[i]: tot[i] / args.steps for i in range(nk) if cnt[i]}}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload_name(args), "global_batch": world * n, "crop": f"{H}x{W}",
+                           "parallelism": f"dp{world}", "l2": "per-step activations (>2 GB) exceed the 126 MB L2",
+                           "collective": "one NCCL all-reduce of the flat fp32 gradient buffer per optimiser step"},
+                "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                        "h2d_bytes_per_step": images_h.numel() * 4 + labels_h.numel() * 8, "d2h_bytes_per_step": 4},
+                "gpu_launches": int(launches), "roofline": roofline}
+        if not args.no_cpu_baseline:
+            cpu_steps = 2 if args.workload == "step1" else 1
+            v, ms, cores = time_cpu(args.workload, 1, cpu_steps, 1)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{cpu_steps} timed + 1 warm-up iterations of the same step at batch 1 on the host CPU "
+                                              f"({ms:.0f} ms/iteration)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

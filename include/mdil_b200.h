@@ -40,6 +40,11 @@ const char* mdil_version(void);
 const char* mdil_last_error_string(void);
 /* Number of kernels this library has launched in this process (host-side counter). */
 unsigned long long mdil_launch_count(void);
+/* Opt-in timing of the fused nb1d pair kernel (bench.py's roofline leg): between begin and end every launch is
+ * bracketed by CUDA events on its own stream; end() synchronises them and returns per-kind totals (HOST arrays).
+ * kind = {C=16,64,128} * 4 + {forward pair 1, forward pair 2, backward pair 2, backward pair 1}. */
+int mdil_profile_begin(void);
+int mdil_profile_end(float* total_ms_host, int* counts_host, int nkinds);
 /* 1 when the running device is compute capability 10.x (the only target built). */
 int mdil_device_supported(int device);
 

@@ -110,6 +110,9 @@ const char* mdil_version(void) { return "mdil_b200 0.1 (sm_100a)"; }
 const char* mdil_last_error_string(void) { return mdil::g_err; }
 unsigned long long mdil_launch_count(void) { return mdil::g_launches.load(std::memory_order_relaxed); }
 
+int mdil_profile_begin(void) { return pair_profile_begin(); }
+int mdil_profile_end(float* total_ms, int* counts, int nkinds) { return pair_profile_end(total_ms, counts, nkinds); }
+
 int mdil_device_supported(int device) {
   cudaDeviceProp p;
   if (cudaGetDeviceProperties(&p, device) != cudaSuccess) return 0;

@@ -101,6 +101,8 @@ struct PairArgs {
   int N, H, W, C, dil, has_adapter, vert_first;
 };
 int launch_pair(const PairArgs& a, cudaStream_t s);
+int pair_profile_begin();
+int pair_profile_end(float* total_ms, int* counts, int nkinds);
 
 // ---------------------------------------------------------------- head_loss.cu
 int launch_outconv_fwd(const float* x, const float* w, const float* bias, float* logits, int N, int H, int W, int Ccls,

@@ -23,7 +23,44 @@
 // register tiles, accumulators never leave registers between the two convolutions' K loops.
 #include "kernels.cuh"
 
+#include <mutex>
+#include <vector>
+
 namespace mdil {
+
+// ---- opt-in per-launch timing of the fused pair kernel (bench.py's roofline leg): CUDA events recorded on the
+// launching stream around each launch while profiling is enabled.  Off by default; host-side state only.
+namespace prof {
+struct Rec { cudaEvent_t a, b; int kind; };
+static std::mutex mu;
+static bool enabled = false;
+static std::vector<Rec> recs;
+}  // namespace prof
+
+int pair_profile_begin() {
+  std::lock_guard<std::mutex> lk(prof::mu);
+  for (auto& r : prof::recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  prof::recs.clear();
+  prof::enabled = true;
+  return 0;
+}
+
+// kinds: 0..11 = (C index {16,64,128}) * 4 + {fwd pair1, fwd pair2, bwd pair2, bwd pair1}
+int pair_profile_end(float* total_ms, int* counts, int nkinds) {
+  std::lock_guard<std::mutex> lk(prof::mu);
+  prof::enabled = false;
+  for (int i = 0; i < nkinds; ++i) { total_ms[i] = 0.f; counts[i] = 0; }
+  for (auto& r : prof::recs) {
+    MDIL_CUDA(cudaEventSynchronize(r.b));
+    float ms = 0.f;
+    MDIL_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+    if (r.kind >= 0 && r.kind < nkinds) { total_ms[r.kind] += ms; counts[r.kind] += 1; }
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  prof::recs.clear();
+  return 0;
+}
 
 namespace {
 
@@ -405,8 +442,22 @@ int launch_pair_c(const PairArgs& a, cudaStream_t s) {
   const long ctas = (long)a.N * cdiv(d * d, ts.TR) * cdiv(Ul, ts.TU) * cdiv(Vl, ts.TV);
   MDIL_REQUIRE(ctas > 0 && ctas < (1L << 31), "pair: grid size");
   MDIL_CUDA(cudaFuncSetAttribute(pair_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D::SMEM_BYTES));
+  prof::Rec rec{nullptr, nullptr, -1};
+  if (prof::enabled) {
+    const int ci = C == 16 ? 0 : (C == 64 ? 1 : 2);
+    const int ph = a.epi == kEpiFwd ? (a.in_scale == nullptr ? 0 : 1) : (a.epi == kEpiBwdMaskStats ? 2 : 3);
+    rec.kind = ci * 4 + ph;
+    MDIL_CUDA(cudaEventCreate(&rec.a));
+    MDIL_CUDA(cudaEventCreate(&rec.b));
+    MDIL_CUDA(cudaEventRecord(rec.a, s));
+  }
   pair_kernel<C><<<(unsigned)ctas, 256, D::SMEM_BYTES, s>>>(a, ts);
   MDIL_LAUNCH_CHECK();
+  if (rec.kind >= 0) {
+    MDIL_CUDA(cudaEventRecord(rec.b, s));
+    std::lock_guard<std::mutex> lk(prof::mu);
+    prof::recs.push_back(rec);
+  }
   return 0;
 }
 

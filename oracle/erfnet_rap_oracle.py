@@ -382,3 +382,27 @@ def perturb_bn_(sd: SD, seed: int = 7) -> SD:
 
 def clone_sd(sd: SD) -> SD:
     return type(sd)((k, v.detach().clone()) for k, v in sd.items())
+
+
+# ------------------------------------------------------------------------ metric
+def iou_add_batch(pred: torch.Tensor, gt: torch.Tensor, n_classes: int, ignore_index: int):
+    """iouEval.addBatch — iouEval.py:21-70, for index inputs [N,1,H,W]: one-hot both, drop the ignore channel,
+    tp = sum x*y, fp = sum x*(1-y-ignores), fn = sum (1-x)*y.  Returns float64 (tp, fp, fn) per class."""
+    x1 = torch.zeros(pred.size(0), n_classes, pred.size(2), pred.size(3)).scatter_(1, pred, 1).float()
+    y1 = torch.zeros(gt.size(0), n_classes, gt.size(2), gt.size(3)).scatter_(1, gt, 1).float()
+    if ignore_index != -1:
+        ignores = y1[:, ignore_index].unsqueeze(1)
+        x1 = x1[:, :ignore_index]
+        y1 = y1[:, :ignore_index]
+    else:
+        ignores = 0
+    tp = (x1 * y1).sum(dim=(0, 2, 3)).double()
+    fp = (x1 * (1 - y1 - ignores)).sum(dim=(0, 2, 3)).double()
+    fn = ((1 - x1) * y1).sum(dim=(0, 2, 3)).double()
+    return tp, fp, fn
+
+
+def iou_from_counts(tp: torch.Tensor, fp: torch.Tensor, fn: torch.Tensor):
+    """iouEval.getIoU — iouEval.py:72-77."""
+    iou = tp / (tp + fp + fn + 1e-15)
+    return torch.mean(iou), iou

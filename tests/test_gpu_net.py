@@ -1,0 +1,203 @@
+"""GPU: whole-network parity against the reference-generated golden fixtures and the oracle: eval logits and
+argmax, train forward/backward (logits, CE, every parameter gradient, BatchNorm buffers), the fused losses,
+a full restated step-2 iteration, the validation metric, and size-independent properties at BASELINE sizes."""
+import numpy as np
+import pytest
+import torch
+
+from _util import assert_close, golden, make_sd, noise_list, oracle
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+DEV = "cuda"
+
+
+def _net(classes, sd, cur_task=None):
+    from mdil_ss_b200.erfnet_RA_parallel import Net
+    net = Net(classes, len(classes), len(classes) - 1 if cur_task is None else cur_task)
+    net.load_state_dict(sd, strict=True)
+    return net.to(DEV)
+
+
+def _to_dev(noise):
+    return [None if t is None else t.to(DEV) for t in noise]
+
+
+@pytest.mark.parametrize("name", ["eval_1task.npz", "eval_3task_t2.npz", "eval_3task_t0.npz"])
+def test_eval_logits_match_reference(name):
+    g = golden(name)
+    classes = [int(c) for c in g["classes"]]
+    net = _net(classes, make_sd(classes, int(g["seed"]), int(g["bn_seed"]))).eval()
+    x = torch.rand(1, 3, 64, 128, generator=torch.Generator().manual_seed(int(g["x_seed"])))
+    with torch.no_grad():
+        y = net(x.to(DEV), int(g["task"]))
+    ref = torch.from_numpy(g["logits"])
+    assert tuple(y.shape) == tuple(ref.shape) and y.is_contiguous()
+    assert_close(y, ref, TOL, name)
+    # indices bit-exact except where the reference's own top-2 margin is below fp32 reordering noise
+    mism = (y.argmax(1).cpu() != ref.argmax(1))
+    if mism.any():
+        top2 = ref.topk(2, dim=1).values
+        margin = (top2[:, 0] - top2[:, 1])[mism]
+        assert float(margin.max()) < 1e-4, f"{int(mism.sum())} argmax mismatches with margin up to {float(margin.max())}"
+
+
+def test_train_forward_backward_matches_reference():
+    g = golden("train_2task_t1.npz")
+    sd = make_sd([20, 20], int(g["init_seed"]), int(g["bn_seed"]))
+    net = _net([20, 20], sd).train()
+    gen = torch.Generator().manual_seed(int(g["x_seed"]))
+    x = torch.rand(2, 3, 32, 64, generator=gen)
+    labels = torch.randint(0, 20, (2, 1, 32, 64), generator=gen)
+    from mdil_ss_b200.losses import CrossEntropyLoss2d
+    crit = CrossEntropyLoss2d(torch.tensor(oracle.WEIGHT_BDD)).to(DEV)
+    logits = net(x.to(DEV), 1, drop_noise=_to_dev(noise_list(g, "noise_")))
+    loss = crit(logits, labels[:, 0].to(DEV))
+    loss.backward()
+    assert_close(logits, torch.from_numpy(g["logits"]), TOL, "logits")
+    assert abs(float(loss) - float(g["loss"])) <= TOL * abs(float(g["loss"]))
+    grads = {n: p.grad for n, p in net.named_parameters() if p.grad is not None}
+    assert list(grads.keys()) == [str(s) for s in g["grad_names"]]
+    gabs = np.array([float(v.double().abs().sum()) for v in grads.values()])
+    np.testing.assert_allclose(gabs, g["grad_abs"], rtol=TOL, atol=1e-4)
+    for i, n in enumerate([str(s) for s in g["pick"]]):
+        assert_close(grads[n], torch.from_numpy(g[f"grad_{i}"]), TOL, n, atol=1e-6)
+    after = net.state_dict()
+    bn_sum = np.array([float(after[str(k)].double().sum()) for k in g["bn_names"]])
+    np.testing.assert_allclose(bn_sum, g["bn_sum"], rtol=1e-4, atol=1e-5)
+
+
+def test_fused_losses_match_reference():
+    from mdil_ss_b200.losses import CrossEntropyLoss2d, OutputKD
+    g = golden("losses.npz")
+    for c, wts in ((20, oracle.WEIGHT_CITY), (27, oracle.WEIGHT_IDD)):
+        lg = torch.from_numpy(g[f"lg{c}"]).to(DEV).requires_grad_(True)
+        loss = CrossEntropyLoss2d(torch.tensor(wts)).to(DEV)(lg, torch.from_numpy(g[f"lb{c}"]).to(DEV))
+        loss.backward()
+        assert abs(float(loss) - float(g[f"ce{c}"])) <= 1e-5 * abs(float(g[f"ce{c}"]))
+        assert_close(lg.grad, torch.from_numpy(g[f"dlg{c}"]), 1e-4, f"dlogits{c}")
+    st = torch.from_numpy(g["st"]).to(DEV).requires_grad_(True)
+    kd = OutputKD()(st, torch.from_numpy(g["te"]).to(DEV))
+    (0.1 * kd).backward()
+    assert abs(float(kd) - float(g["kd"])) <= 1e-5 * abs(float(g["kd"]))
+    assert_close(st.grad, 0.1 * torch.from_numpy(g["dst"]), 1e-4, "dstudent")
+
+
+def test_step2_iteration_matches_reference():
+    from mdil_ss_b200.train_step import Step2Trainer
+    g = golden("step2_iter.npz")
+    sd_new = make_sd([20, 20], 10, 14)
+    teacher = _net([20], make_sd([20], 9, 13))
+    student = _net([20, 20], sd_new)
+    gen = torch.Generator().manual_seed(400)
+    x = torch.rand(2, 3, 32, 64, generator=gen).to(DEV)
+    labels = torch.randint(0, 20, (2, 1, 32, 64), generator=gen).to(DEV)
+    tr = Step2Trainer(student, teacher, torch.tensor(oracle.WEIGHT_BDD, device=DEV), 1, 0.1)
+    # replay the reference's Dropout2d stream: first forward (task 1) then second forward (task 0)
+    streams = [_to_dev(noise_list(g, "noise_t_")), _to_dev(noise_list(g, "noise_prev_"))]
+    orig = student.forward
+    calls = []
+
+    def fwd(inp, task, drop_noise=None):
+        calls.append(task)
+        return orig(inp, task, drop_noise=streams[len(calls) - 1])
+
+    student.forward = fwd
+    total, ce, kd = tr.step(x, labels)
+    assert calls == [1, 0]
+    assert abs(float(ce) - float(g["ce"])) <= TOL * abs(float(g["ce"]))
+    assert abs(float(kd) - float(g["kd"])) <= TOL * abs(float(g["kd"]))
+    assert abs(float(total) - float(g["total"])) <= TOL * abs(float(g["total"]))
+    names = [str(s) for s in g["grad_names"]]
+    grads = {n: p.grad for n, p in student.named_parameters() if p.requires_grad}
+    assert sorted(names) == sorted(grads.keys())
+    gabs = np.array([float(grads[n].double().abs().sum()) for n in names])
+    np.testing.assert_allclose(gabs, g["grad_abs"], rtol=2e-3, atol=1e-4)
+    # post-step parameters.  Adam's first update is lr * g / (|g| + eps): parameters whose gradient is
+    # mathematically zero (biases feeding a train-mode BatchNorm) move by rounding noise, so they are skipped.
+    after = student.state_dict()
+    gref = dict(zip(names, g["grad_abs"]))
+    for k, ref_delta in zip([str(s) for s in g["after_names"]], g["delta_abs"]):
+        if k in gref and gref[k] < 1e-3:
+            continue
+        if "running" in k or "num_batches" in k:
+            continue
+        d = float((after[k].double().cpu() - sd_new[k].double()).abs().sum())
+        assert abs(d - ref_delta) <= 2e-2 * ref_delta + 1e-6, f"{k}: |delta| {d} vs reference {ref_delta}"
+
+
+def test_miou_parity_with_reference_metric():
+    from mdil_ss_b200.iou import iouEval
+    g = golden("eval_3task_t2.npz")
+    classes = [int(c) for c in g["classes"]]
+    net = _net(classes, make_sd(classes, int(g["seed"]), int(g["bn_seed"]))).eval()
+    gen = torch.Generator().manual_seed(17)
+    x = torch.rand(2, 3, 64, 128, generator=gen)
+    labels = torch.randint(0, 27, (2, 1, 64, 128), generator=gen)
+    with torch.no_grad():
+        logits = net(x.to(DEV), 2)
+        ref_logits = oracle.net_forward(make_sd(classes, int(g["seed"]), int(g["bn_seed"])), x, 2, False)
+    ev = iouEval(27, 26)
+    ev.addLogits(logits, labels.to(DEV))
+    tp, fp, fn = oracle.iou_add_batch(ref_logits.max(1)[1].unsqueeze(1), labels, 27, 26)
+    n_mismatch = int((logits.argmax(1).cpu() != ref_logits.argmax(1)).sum())
+    if n_mismatch == 0:
+        assert torch.equal(ev.tp, tp) and torch.equal(ev.fp, fp) and torch.equal(ev.fn, fn)
+    miou, _ = ev.getIoU()
+    miou_ref, _ = oracle.iou_from_counts(tp, fp, fn)
+    assert abs(float(miou) - float(miou_ref)) <= 1e-4 + 2.0 * n_mismatch / labels.numel()
+    # reference-signature path on the same predictions
+    ev2 = iouEval(27, 26)
+    ev2.addBatch(logits.max(1)[1].unsqueeze(1).cpu(), labels)
+    assert torch.equal(ev2.tp, ev.tp) and torch.equal(ev2.fp, ev.fp) and torch.equal(ev2.fn, ev.fn)
+
+
+# ------------------------------------------------------------------------------ properties at BASELINE sizes
+def test_full_size_shapes_and_batch_independence():
+    """512x1024 (Plot_Tsne_Notebook.ipynb:488,513 shape contract): logits [N,20,512,1024], encoder [N,128,64,128];
+    in eval mode a crop's logits do not depend on its batch neighbours."""
+    torch.manual_seed(0)
+    net = _net([20], make_sd([20], 0, 7)).eval()
+    x = torch.rand(2, 3, 512, 1024, device=DEV)
+    with torch.no_grad():
+        enc = net.encoder(x)
+        y = net(x, 0)
+        y0 = net(x[:1].contiguous(), 0)
+    assert tuple(enc.shape) == (2, 128, 64, 128)
+    assert tuple(y.shape) == (2, 20, 512, 1024)
+    assert torch.isfinite(y).all()
+    assert torch.equal(y[:1], y0)
+
+
+def test_full_size_loss_properties():
+    from mdil_ss_b200.losses import CrossEntropyLoss2d, OutputKD
+    n, c, h, w = 2, 20, 512, 1024
+    wts = torch.tensor(oracle.WEIGHT_CITY, device=DEV)
+    labels = torch.randint(0, c, (n, h, w), device=DEV)
+    flat = torch.zeros(n, c, h, w, device=DEV, requires_grad=True)
+    loss = CrossEntropyLoss2d(wts)(flat, labels)
+    loss.backward()
+    assert abs(float(loss) - float(np.log(c))) < 1e-5          # uniform logits: CE = log C whatever the weights
+    assert float(flat.grad.sum(1).abs().max()) < 1e-9           # softmax-minus-onehot rows sum to zero
+    ign = (labels == c - 1)
+    assert float(flat.grad[:, :, :, :].permute(0, 2, 3, 1)[ign].abs().max()) == 0.0   # zero-weight class = ignored
+    s = torch.randn(n, c, h, w, device=DEV, requires_grad=True)
+    kd = OutputKD()(s, s.detach())
+    kd.backward()
+    assert float(s.grad.sum(1).abs().max()) < 1e-9
+    assert float(kd) < 0
+    shifted = OutputKD()(s.detach() + 3.0, s.detach() - 2.0)    # softmax shift invariance
+    assert abs(float(shifted) - float(kd)) < 1e-6
+
+
+def test_full_size_train_step_runs_and_decreases_loss():
+    from mdil_ss_b200.erfnet_RA_parallel import Net
+    from mdil_ss_b200.train_step import Step1Trainer, class_weights
+    torch.manual_seed(0)
+    net = Net([20], 1, 0).to(DEV)
+    tr = Step1Trainer(net, class_weights("cityscapes", DEV))
+    x = torch.rand(2, 3, 512, 1024, device=DEV)
+    labels = torch.randint(0, 20, (2, 1, 16, 32), device=DEV).repeat_interleave(32, 2).repeat_interleave(32, 3)
+    losses = [float(tr.step(x, labels)) for _ in range(6)]
+    assert all(np.isfinite(losses))
+    assert losses[-1] < losses[0]

@@ -1,0 +1,109 @@
+"""CPU: host-side logic — the drop-in module contract (state_dict keys, shapes, parameter order, default init),
+name-based freezing / param-group policy, the C-ABI library (loads and exports every symbol the header declares;
+no compute calls without a GPU), loud failure without CUDA, the IoU bookkeeping."""
+import ctypes
+import json
+import os
+import re
+
+import pytest
+import torch
+
+from _util import GOLDEN, REPO, oracle
+
+
+def _contract():
+    return json.load(open(os.path.join(GOLDEN, "contract.json")))
+
+
+@pytest.mark.parametrize("classes", [[20], [20, 20], [20, 20, 27]])
+def test_module_contract_matches_reference(classes, capsys):
+    from models.erfnet_RA_parallel import Net
+    c = _contract()[str(len(classes))]
+    torch.manual_seed(0)
+    net = Net(classes, len(classes), len(classes) - 1)
+    assert "hi, inside erfnet_RA_parallel" in capsys.readouterr().out  # reference prints this (:201)
+    sd = net.state_dict()
+    assert list(sd.keys()) == c["keys"]
+    assert [list(v.shape) for v in sd.values()] == c["shapes"]
+    assert [n for n, _ in net.named_parameters()] == c["params"]
+    cs = float(sum(v.double().sum() for v in sd.values() if v.dtype.is_floating_point))
+    assert abs(cs - c["checksum"]) <= 1e-9 * max(1.0, abs(c["checksum"]))  # same RNG consumption at init
+    assert isinstance(str(net), str) and len(str(net)) > 1000
+    assert hasattr(net.encoder, "initial_block") and len(net.encoder.layers) == 15
+    assert len(net.decoder) == len(classes) and len(net.decoder[0].layers) == 6
+
+
+def test_forward_sets_the_module_global_like_the_reference():
+    import mdil_ss_b200.erfnet_RA_parallel as M
+    net = M.Net([20, 20], 2, 1)
+    assert M.current_task == 1
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(1, 3, 16, 32), 0)   # CPU tensor: loud failure, never a fallback
+    assert M.current_task == 0
+
+
+def test_freeze_policy_and_param_groups():
+    from mdil_ss_b200.erfnet_RA_parallel import Net
+    from mdil_ss_b200 import train_step as T
+    net = Net([20, 20, 27], 3, 2)
+    T.apply_incremental_freeze(net, 2)
+    sd = oracle.init_state_dict([20, 20, 27], 3, seed=0)
+    trainable = [n for n, p in net.named_parameters() if p.requires_grad]
+    assert trainable == oracle.trainable_names_incremental(sd, 2)
+    assert sum(p.numel() for p in net.parameters() if p.requires_grad) == 2370503   # SURVEY.md §5 [probe]
+    groups = T.incremental_param_groups(net, 2)
+    names = dict((id(p), n) for n, p in net.named_parameters())
+    shared = [names[id(p)] for p in groups[0]["params"]]
+    assert all(oracle.is_shared(n) for n in shared) and groups[0]["lr"] == 5e-6
+    assert sum(p.numel() for p in groups[0]["params"]) == 1868252
+    assert all(oracle.is_ds_curr(names[id(p)], 2) for p in groups[1]["params"])
+    assert abs(T.poly_lr_factor(1, 150) - 1.0) < 1e-12 and abs(T.poly_lr_factor(76, 150) - oracle.poly_lr_factor(76, 150)) < 1e-15
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from mdil_ss_b200 import _lib
+    header = open(os.path.join(REPO, "include", "mdil_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(mdil_[a-z0-9_]+)\s*\(", header)))
+    assert len(declared) >= 25
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(handle, name), f"{name} declared in include/mdil_b200.h but not exported"
+    assert sorted(set(_lib.EXPORTS)) == declared
+    lib = _lib.lib()
+    assert b"sm_100a" in lib.mdil_version()
+    assert lib.mdil_nb1d_packed_floats(128) == 28 * 128 * 128
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from mdil_ss_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libmdil_b200.so")
+    with pytest.raises(RuntimeError, match="no CPU or PyTorch fallback"):
+        _lib.lib()
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(REPO, "mdil_ss_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(root, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f"{f} imports oracle/"
+
+
+def test_iou_bookkeeping_matches_reference_metric():
+    from mdil_ss_b200.iou import iouEval
+    g = torch.Generator().manual_seed(3)
+    pred = torch.randint(0, 20, (2, 1, 24, 40), generator=g)
+    gt = torch.randint(0, 20, (2, 1, 24, 40), generator=g)
+    ev = iouEval(20, 19)
+    ev.addBatch(pred, gt)
+    tp, fp, fn = oracle.iou_add_batch(pred, gt, 20, 19)
+    assert torch.equal(ev.tp, tp) and torch.equal(ev.fp, fp) and torch.equal(ev.fn, fn)
+    m, per = ev.getIoU()
+    m2, per2 = oracle.iou_from_counts(tp, fp, fn)
+    assert torch.equal(per, per2) and float(m) == float(m2)

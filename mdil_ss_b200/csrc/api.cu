@@ -6,6 +6,7 @@
 
 #include <atomic>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace mdil {
@@ -241,6 +242,9 @@ int mdil_nb1d_bwd(const mdil_nb1d_desc* d, const float* dy, const float* x, cons
   MDIL_TRY(launch_bn_bwd_stats(dy, y, drop_mask, sv->s, st2, sums2, N, HW, C, s));
   MDIL_TRY(launch_bn_bwd_finalize(sums2, count, C, w->bn2.weight, st2, coef2, gr->bn2_w, gr->bn2_b, s));
   MDIL_TRY(launch_bn_bwd_apply(dy, y, drop_mask, sv->s, st2, coef2, T1, N, HW, C, s));
+  const char* dbg = getenv("MDIL_DEBUG_STOP");
+  const int stop = dbg ? atoi(dbg) : 0;
+  if (stop == 1) return 0;
 
   // ---- pair 2 backward: ds -> dc' -> dq (masked by r>0), sums for BN1 backward
   PairArgs a;
@@ -249,6 +253,7 @@ int mdil_nb1d_bwd(const mdil_nb1d_desc* d, const float* dy, const float* x, cons
   a.in = T1; a.wstream = packed + 14 * CC; a.mid_mask = sv->c; a.mid_out = T2; a.out = T3;
   a.epi = kEpiBwdMaskStats; a.e0 = sv->p; a.e_stats = st1; a.sums = sums1; a.dil = d->dil;
   MDIL_TRY(launch_pair(a, s));
+  if (stop == 2) return 0;
 
   // ---- weight gradients of pair 2
   {
@@ -259,6 +264,7 @@ int mdil_nb1d_bwd(const mdil_nb1d_desc* d, const float* dy, const float* x, cons
     MDIL_TRY(nb1d_wgrad(gv, sv->p, st1 + 2 * C, st1 + 3 * C, T2, gr->w31_2, gr->b31_2, C, 3, s));
   }
 
+  if (stop == 3) return 0;
   // ---- BN1 backward: dq -> dp (overwrites ds)
   MDIL_TRY(launch_bn_bwd_finalize(sums1, count, C, w->bn1.weight, st1, coef1, gr->bn1_w, gr->bn1_b, s));
   MDIL_TRY(launch_bn_bwd_apply(T3, nullptr, nullptr, sv->p, st1, coef1, T1, N, HW, C, s));

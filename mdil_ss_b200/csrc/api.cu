@@ -125,13 +125,33 @@ int mdil_nchw_to_nhwc4(const float* x, float* y, int N, int C, int H, int W, voi
 }
 
 // =============================================================================== nb1d
-size_t mdil_nb1d_packed_floats(int C) { return (size_t)28 * C * C; }
+// [0, 28 C^2): fp32 streams of the FFMA kernel; [28 C^2, 84 C^2): hi/lo images of the tensor-core kernel (4 x 14 C^2)
+size_t mdil_nb1d_packed_floats(int C) { return (size_t)84 * C * C; }
+
+static bool use_tensor_cores(int C) {
+  static const int mode = [] {
+    const char* e = getenv("MDIL_PAIR_IMPL");
+    return (e != nullptr && strcmp(e, "ffma") == 0) ? 0 : 1;
+  }();
+  return mode == 1 && (C == 64 || C == 128);
+}
+static bool use_tc_wgrad(int C) {
+  static const int mode = [] {
+    const char* e = getenv("MDIL_WGRAD_IMPL");
+    return (e != nullptr && strcmp(e, "ffma") == 0) ? 0 : 1;
+  }();
+  return mode == 1 && (C == 64 || C == 128);
+}
+static inline const float* tc_stream(const float* packed, int C, int which) {
+  return use_tensor_cores(C) ? packed + (size_t)28 * C * C + (size_t)which * 14 * C * C : nullptr;
+}
 
 size_t mdil_nb1d_fwd_workspace_bytes(const mdil_nb1d_desc* d) { return 256 + (size_t)4 * d->C * sizeof(double) + 256; }
 
 size_t mdil_nb1d_bwd_workspace_bytes(const mdil_nb1d_desc* d) {
   size_t T = align_up((size_t)d->N * d->H * d->W * d->C * sizeof(float), 256);
-  return 3 * T + (size_t)4 * d->C * sizeof(double) + (size_t)6 * d->C * sizeof(float) + 8 * 256;
+  return 3 * T + (size_t)4 * d->C * sizeof(double) + (size_t)6 * d->C * sizeof(float) +
+         (size_t)3 * d->C * d->C * sizeof(float) + 10 * 256;
 }
 
 int mdil_nb1d_pack(const mdil_nb1d_desc* d, const mdil_nb1d_weights* w, float* packed, void* stream) {
@@ -155,6 +175,11 @@ int mdil_nb1d_pack(const mdil_nb1d_desc* d, const mdil_nb1d_weights* w, float* p
     MDIL_TRY(launch_pack(w->wp2, packed + 13 * CC, 1, C, C, C, C, 1, C, 0, 0, s));
     MDIL_TRY(launch_pack(w->wp2, packed + 20 * CC, 1, C, C, C, C, C, 1, 0, 0, s));   // [co][ci]
     MDIL_TRY(launch_pack(w->wp1, packed + 27 * CC, 1, C, C, C, C, C, 1, 0, 0, s));
+  }
+  if (use_tensor_cores(C)) {
+    for (int which = 0; which < 4; ++which)
+      MDIL_TRY(launch_pack_tc(packed + (size_t)which * 7 * CC, packed + 28 * CC + (size_t)which * 14 * CC, C,
+                              d->has_adapter, s));
   }
   return 0;
 }
@@ -182,13 +207,13 @@ int mdil_nb1d_fwd(const mdil_nb1d_desc* d, const float* x, const mdil_nb1d_weigh
   memset(&a, 0, sizeof(a));
   a.N = d->N; a.H = d->H; a.W = d->W; a.C = C; a.has_adapter = d->has_adapter; a.vert_first = 1; a.epi = kEpiFwd;
   // pair 1: x -> a -> p
-  a.in = x; a.wstream = packed; a.b1 = w->b31_1; a.b2 = w->b13_1; a.bad = d->has_adapter ? w->bp1 : nullptr;
+  a.in = x; a.wstream = packed; a.wstream_tc = tc_stream(packed, C, 0); a.b1 = w->b31_1; a.b2 = w->b13_1; a.bad = d->has_adapter ? w->bp1 : nullptr;
   a.mid_out = d->save ? sv->a : nullptr; a.out = sv->p; a.sums = d->train ? sums1 : nullptr; a.dil = 1;
   MDIL_TRY(launch_pair(a, s));
   MDIL_TRY(launch_bn_finalize(sums1, C, count, C, w->bn1.weight, w->bn1.bias, w->bn1.running_mean, w->bn1.running_var,
                               d->eps, d->momentum, d->train, st1, s));
   // pair 2: r = relu(bn1(p)) -> c -> s
-  a.in = sv->p; a.in_scale = st1 + 2 * C; a.in_shift = st1 + 3 * C; a.wstream = packed + 7 * CC;
+  a.in = sv->p; a.in_scale = st1 + 2 * C; a.in_shift = st1 + 3 * C; a.wstream = packed + 7 * CC; a.wstream_tc = tc_stream(packed, C, 1);
   a.b1 = w->b31_2; a.b2 = w->b13_2; a.bad = d->has_adapter ? w->bp2 : nullptr;
   a.mid_out = d->save ? sv->c : nullptr; a.out = sv->s; a.sums = d->train ? sums2 : nullptr; a.dil = d->dil;
   MDIL_TRY(launch_pair(a, s));
@@ -199,16 +224,29 @@ int mdil_nb1d_fwd(const mdil_nb1d_desc* d, const float* x, const mdil_nb1d_weigh
   return 0;
 }
 
-static int nb1d_wgrad(const ConvGeom& g, const float* A, const float* sc, const float* sh, const float* G, float* dW,
-                      float* db, int C, int taps, cudaStream_t s) {
+// One weight gradient of the block: tensor-core path (C = 64, 128) or the generic FFMA tap kernel.
+// taps: 3 (vertical when vert != 0, else horizontal, dilation d) or 1 (1x1 adapter).
+static int nb1d_wgrad(const mdil_nb1d_desc* d, int dil, bool vert, int taps, const float* A, const float* sc,
+                      const float* sh, const float* G, float* dW, float* db, float* acc_scratch, cudaStream_t s) {
+  const int C = d->C;
   if (dW == nullptr) {
     MDIL_REQUIRE(db == nullptr, "nb1d_bwd: bias gradient without weight gradient is not supported");
     return 0;
   }
-  MDIL_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)C * C * taps, s));
   if (db != nullptr) MDIL_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * C, s));
-  // torch layout [co][ci][taps]
-  return launch_wgrad_taps(g, A, sc, sh, G, dW, taps, (long)C * taps, taps == 1 ? 0 : 1, db, s);
+  const long s_ci = taps, s_co = (long)C * taps, s_t = taps == 1 ? 0 : 1;   // torch layout [co][ci][taps]
+  if (use_tc_wgrad(C)) {
+    MDIL_CUDA(cudaMemsetAsync(acc_scratch, 0, sizeof(float) * (size_t)C * C * taps, s));
+    WgradTcArgs w;
+    memset(&w, 0, sizeof(w));
+    w.A = A; w.a_scale = sc; w.a_shift = sh; w.G = G; w.dWacc = acc_scratch; w.db = db;
+    w.N = d->N; w.H = d->H; w.W = d->W; w.C = C; w.dil = dil; w.ntaps = taps; w.vert = vert ? 1 : 0;
+    MDIL_TRY(launch_wgrad_tc(w, s));
+    return launch_wgrad_unpack(acc_scratch, dW, C, taps, s_ci, s_co, s_t, s);
+  }
+  MDIL_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)C * C * taps, s));
+  ConvGeom g = taps == 1 ? pointwise_geom(d->N, d->H, d->W, C) : taps3_geom(d->N, d->H, d->W, C, dil, vert);
+  return launch_wgrad_taps(g, A, sc, sh, G, dW, s_ci, s_co, s_t, db, s);
 }
 
 int mdil_nb1d_bwd(const mdil_nb1d_desc* d, const float* dy, const float* x, const float* y, const mdil_nb1d_weights* w,
@@ -233,6 +271,7 @@ int mdil_nb1d_bwd(const mdil_nb1d_desc* d, const float* dy, const float* x, cons
   float* T1 = cv.take<float>(T);
   float* T2 = cv.take<float>(T);
   float* T3 = cv.take<float>(T);
+  float* wacc = cv.take<float>((size_t)3 * C * C);   // tensor-core weight-gradient accumulator [3][C][C]
   const float* st1 = sv->stats;
   const float* st2 = sv->stats + 4 * C;
   MDIL_CUDA(cudaMemsetAsync(sums2, 0, 2 * C * sizeof(double), s));
@@ -250,19 +289,16 @@ int mdil_nb1d_bwd(const mdil_nb1d_desc* d, const float* dy, const float* x, cons
   PairArgs a;
   memset(&a, 0, sizeof(a));
   a.N = N; a.H = H; a.W = W; a.C = C; a.has_adapter = d->has_adapter; a.vert_first = 0;
-  a.in = T1; a.wstream = packed + 14 * CC; a.mid_mask = sv->c; a.mid_out = T2; a.out = T3;
+  a.in = T1; a.wstream = packed + 14 * CC; a.wstream_tc = tc_stream(packed, C, 2); a.mid_mask = sv->c; a.mid_out = T2; a.out = T3;
   a.epi = kEpiBwdMaskStats; a.e0 = sv->p; a.e_stats = st1; a.sums = sums1; a.dil = d->dil;
   MDIL_TRY(launch_pair(a, s));
   if (stop == 2) return 0;
 
   // ---- weight gradients of pair 2
-  {
-    ConvGeom gh = taps3_geom(N, H, W, C, d->dil, false), gv = taps3_geom(N, H, W, C, d->dil, true);
-    ConvGeom gp = pointwise_geom(N, H, W, C);
-    MDIL_TRY(nb1d_wgrad(gh, sv->c, nullptr, nullptr, T1, gr->w13_2, gr->b13_2, C, 3, s));
-    if (d->has_adapter) MDIL_TRY(nb1d_wgrad(gp, sv->p, st1 + 2 * C, st1 + 3 * C, T1, gr->wp2, gr->bp2, C, 1, s));
-    MDIL_TRY(nb1d_wgrad(gv, sv->p, st1 + 2 * C, st1 + 3 * C, T2, gr->w31_2, gr->b31_2, C, 3, s));
-  }
+  MDIL_TRY(nb1d_wgrad(d, d->dil, false, 3, sv->c, nullptr, nullptr, T1, gr->w13_2, gr->b13_2, wacc, s));
+  if (d->has_adapter)
+    MDIL_TRY(nb1d_wgrad(d, 1, true, 1, sv->p, st1 + 2 * C, st1 + 3 * C, T1, gr->wp2, gr->bp2, wacc, s));
+  MDIL_TRY(nb1d_wgrad(d, d->dil, true, 3, sv->p, st1 + 2 * C, st1 + 3 * C, T2, gr->w31_2, gr->b31_2, wacc, s));
 
   if (stop == 3) return 0;
   // ---- BN1 backward: dq -> dp (overwrites ds)
@@ -270,18 +306,14 @@ int mdil_nb1d_bwd(const mdil_nb1d_desc* d, const float* dy, const float* x, cons
   MDIL_TRY(launch_bn_bwd_apply(T3, nullptr, nullptr, sv->p, st1, coef1, T1, N, HW, C, s));
 
   // ---- pair 1 backward: dp -> da' -> dx (+ residual dy * (y>0))
-  a.in = T1; a.wstream = packed + 21 * CC; a.mid_mask = sv->a; a.mid_out = T2; a.out = dx;
+  a.in = T1; a.wstream = packed + 21 * CC; a.wstream_tc = tc_stream(packed, C, 3); a.mid_mask = sv->a; a.mid_out = T2; a.out = dx;
   a.epi = kEpiBwdResidual; a.e0 = dy; a.e1 = y; a.e_stats = nullptr; a.sums = nullptr; a.dil = 1;
   MDIL_TRY(launch_pair(a, s));
 
   // ---- weight gradients of pair 1
-  {
-    ConvGeom gh = taps3_geom(N, H, W, C, 1, false), gv = taps3_geom(N, H, W, C, 1, true);
-    ConvGeom gp = pointwise_geom(N, H, W, C);
-    MDIL_TRY(nb1d_wgrad(gh, sv->a, nullptr, nullptr, T1, gr->w13_1, gr->b13_1, C, 3, s));
-    if (d->has_adapter) MDIL_TRY(nb1d_wgrad(gp, x, nullptr, nullptr, T1, gr->wp1, gr->bp1, C, 1, s));
-    MDIL_TRY(nb1d_wgrad(gv, x, nullptr, nullptr, T2, gr->w31_1, gr->b31_1, C, 3, s));
-  }
+  MDIL_TRY(nb1d_wgrad(d, 1, false, 3, sv->a, nullptr, nullptr, T1, gr->w13_1, gr->b13_1, wacc, s));
+  if (d->has_adapter) MDIL_TRY(nb1d_wgrad(d, 1, true, 1, x, nullptr, nullptr, T1, gr->wp1, gr->bp1, wacc, s));
+  MDIL_TRY(nb1d_wgrad(d, 1, true, 3, x, nullptr, nullptr, T2, gr->w31_1, gr->b31_1, wacc, s));
   return 0;
 }
 

@@ -87,6 +87,7 @@ struct PairArgs {
   const float* in_scale;   // nullable: prologue v = relu(v*scale+shift)
   const float* in_shift;
   const float* wstream;    // packed [3][C][C] first conv, [3][C][C] second conv, [C][C] adapter (if has_adapter)
+  const float* wstream_tc; // tensor-core path: hi/lo SWIZZLE_64B chunk images (conv 1, adapter, conv 2) or NULL
   const float* b1;         // nullable
   const float* b2;         // nullable
   const float* bad;        // nullable (adapter bias)
@@ -99,10 +100,29 @@ struct PairArgs {
   const float* e_stats;    // epi1: [4][C] mean, invstd, scale, shift of BN1
   double* sums;            // nullable: [2][C] (fwd: sum out, sum out^2; epi1: sum out, sum out*phat)
   int N, H, W, C, dil, has_adapter, vert_first;
+  int trace;               // debug: CTA 0 prints its phase timestamps (MDIL_TC_TRACE=1)
 };
-int launch_pair(const PairArgs& a, cudaStream_t s);
+int launch_pair(const PairArgs& a, cudaStream_t s);          // dispatch: tensor-core kernel when wstream_tc != NULL
+int launch_pair_ffma(const PairArgs& a, cudaStream_t s);     // nb1d_pair.cu (FP32 FFMA; all C)
+int launch_pair_tc(const PairArgs& a, cudaStream_t s);       // nb1d_pair_tc.cu (tcgen05 3xTF32; C = 64, 128)
+int launch_pack_tc(const float* src_stream, float* dst_stream, int C, int has_adapter, cudaStream_t s);
+void pair_profile_record_begin(const PairArgs& a, cudaStream_t s, void** rec);
+void pair_profile_record_end(cudaStream_t s, void* rec);
 int pair_profile_begin();
 int pair_profile_end(float* total_ms, int* counts, int nkinds);
+
+// ---------------------------------------------------------------- wgrad_tc.cu
+struct WgradTcArgs {
+  const float* A;          // activation [N,H,W,C]
+  const float* a_scale;    // nullable: A' = relu(A*scale+shift)
+  const float* a_shift;
+  const float* G;          // gradient [N,H,W,C]
+  float* dWacc;            // [ntaps][C(ci)][C(co)] fp32, zeroed by the caller (accumulated with red.global.add)
+  float* db;               // nullable [C], zeroed by the caller
+  int N, H, W, C, dil, ntaps, vert;
+};
+int launch_wgrad_tc(const WgradTcArgs& a, cudaStream_t s);
+int launch_wgrad_unpack(const float* acc, float* dW, int C, int ntaps, long s_ci, long s_co, long s_t, cudaStream_t s);
 
 // ---------------------------------------------------------------- head_loss.cu
 int launch_outconv_fwd(const float* x, const float* w, const float* bias, float* logits, int N, int H, int W, int Ccls,

@@ -24,6 +24,7 @@
 #include "kernels.cuh"
 
 #include <mutex>
+#include <stdlib.h>
 #include <vector>
 
 namespace mdil {
@@ -60,6 +61,27 @@ int pair_profile_end(float* total_ms, int* counts, int nkinds) {
   }
   prof::recs.clear();
   return 0;
+}
+
+void pair_profile_record_begin(const PairArgs& a, cudaStream_t s, void** out) {
+  *out = nullptr;
+  if (!prof::enabled) return;
+  prof::Rec* rec = new prof::Rec{nullptr, nullptr, -1};
+  const int ci = a.C == 16 ? 0 : (a.C == 64 ? 1 : 2);
+  const int ph = a.epi == kEpiFwd ? (a.in_scale == nullptr ? 0 : 1) : (a.epi == kEpiBwdMaskStats ? 2 : 3);
+  rec->kind = ci * 4 + ph;
+  if (cudaEventCreate(&rec->a) != cudaSuccess || cudaEventCreate(&rec->b) != cudaSuccess) { delete rec; return; }
+  cudaEventRecord(rec->a, s);
+  *out = rec;
+}
+
+void pair_profile_record_end(cudaStream_t s, void* p) {
+  if (p == nullptr) return;
+  prof::Rec* rec = static_cast<prof::Rec*>(p);
+  cudaEventRecord(rec->b, s);
+  std::lock_guard<std::mutex> lk(prof::mu);
+  prof::recs.push_back(*rec);
+  delete rec;
 }
 
 namespace {
@@ -442,28 +464,25 @@ int launch_pair_c(const PairArgs& a, cudaStream_t s) {
   const long ctas = (long)a.N * cdiv(d * d, ts.TR) * cdiv(Ul, ts.TU) * cdiv(Vl, ts.TV);
   MDIL_REQUIRE(ctas > 0 && ctas < (1L << 31), "pair: grid size");
   MDIL_CUDA(cudaFuncSetAttribute(pair_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D::SMEM_BYTES));
-  prof::Rec rec{nullptr, nullptr, -1};
-  if (prof::enabled) {
-    const int ci = C == 16 ? 0 : (C == 64 ? 1 : 2);
-    const int ph = a.epi == kEpiFwd ? (a.in_scale == nullptr ? 0 : 1) : (a.epi == kEpiBwdMaskStats ? 2 : 3);
-    rec.kind = ci * 4 + ph;
-    MDIL_CUDA(cudaEventCreate(&rec.a));
-    MDIL_CUDA(cudaEventCreate(&rec.b));
-    MDIL_CUDA(cudaEventRecord(rec.a, s));
-  }
   pair_kernel<C><<<(unsigned)ctas, 256, D::SMEM_BYTES, s>>>(a, ts);
   MDIL_LAUNCH_CHECK();
-  if (rec.kind >= 0) {
-    MDIL_CUDA(cudaEventRecord(rec.b, s));
-    std::lock_guard<std::mutex> lk(prof::mu);
-    prof::recs.push_back(rec);
-  }
   return 0;
 }
 
 }  // namespace
 
-int launch_pair(const PairArgs& a, cudaStream_t s) {
+int launch_pair(const PairArgs& a_in, cudaStream_t s) {
+  static const int trace = getenv("MDIL_TC_TRACE") != nullptr ? 1 : 0;
+  PairArgs a = a_in;
+  a.trace = trace;
+  void* rec = nullptr;
+  pair_profile_record_begin(a, s, &rec);
+  const int rc = (a.wstream_tc != nullptr && (a.C == 64 || a.C == 128)) ? launch_pair_tc(a, s) : launch_pair_ffma(a, s);
+  pair_profile_record_end(s, rec);
+  return rc;
+}
+
+int launch_pair_ffma(const PairArgs& a, cudaStream_t s) {
   MDIL_REQUIRE(a.dil >= 1 && a.N > 0 && a.H > 0 && a.W > 0, "pair: bad dims");
   MDIL_REQUIRE(((uintptr_t)a.wstream & 15) == 0, "pair: weight stream must be 16-byte aligned");
   switch (a.C) {

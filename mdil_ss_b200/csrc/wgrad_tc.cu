@@ -1,0 +1,353 @@
+// Tensor-core (tcgen05 / TMEM) weight-gradient kernel of the nb1d block's 3-tap and 1x1 convolutions, C = 64 / 128:
+//     dW[t][ci][co] = sum_pixels A'[pix + (t-1)*d along the tap axis][ci] * G[pix][co],     db[co] = sum_pixels G[pix][co]
+// (B2 of SURVEY appendix: a [C x 3C] reduction over all N*h*w pixels).  A' = A or ReLU(A*scale+shift).
+//
+// GEMM view: M = ci, N = co, K = pixels.  The NHWC activation layout IS the MN-major operand layout of the UMMA
+// (one 128-byte row per pixel and 32-channel slab, SWIZZLE_128B_BASE32B), so tiles are staged with plain coalesced
+// 128-bit loads, split into hi/lo TF32 parts (3xTF32, fp32 accumulate) and never transposed.  Pixels are walked in
+// the d-strided lattice along the tap axis, 16 perpendicular pixels per chunk: the three taps of gradient chunk j
+// are then the activation chunks j-1, j, j+1 already in the shared-memory ring.  Accumulators (3 x [C x C] fp32)
+// stay in TMEM for the whole life of the persistent CTA and leave through vectorised red.global.add.v4.f32.
+//
+// Warp roles: warps 0-7 producers (two groups of 4 warps fill alternate ring stages), warp 8 lane 0 issues the MMAs.
+#include "kernels.cuh"
+
+namespace mdil {
+namespace wtc {
+
+constexpr int TP = 16;        // pixels per chunk (= 2 K-steps of 8)
+constexpr int NWORK = 256;
+
+template <int C> struct Cfg {
+  static constexpr int NST = C == 128 ? 6 : 8;                 // ring stages
+  static constexpr uint32_t PART = C * TP * 4;                  // one of A_hi, A_lo, G_hi, G_lo
+  static constexpr uint32_t STAGE = 4 * PART;
+  static constexpr uint32_t SLAB = TP * 128;                    // 32-channel slab stride (LBO)
+  static constexpr uint32_t HDR = 1024;
+  static constexpr uint32_t SMEM = 1024 + HDR + NST * STAGE;
+  static constexpr int TMEM_COLS = C == 128 ? 512 : 256;        // 3 accumulators of C columns, power of two
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc),
+      "r"(acc) : "memory");
+}
+// MN-major operand, SWIZZLE_128B_BASE32B (32-bit elements): LBO = stride between 32-channel groups, SBO = 512 (4 pixel rows)
+__device__ __forceinline__ uint64_t desc_mn(uint32_t saddr, uint32_t lbo) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)1 << 61);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void split4(const float4& x, float4& hi, float4& lo) {
+  hi.x = tf32_rna(x.x); hi.y = tf32_rna(x.y); hi.z = tf32_rna(x.z); hi.w = tf32_rna(x.w);
+  lo.x = tf32_rna(x.x - hi.x); lo.y = tf32_rna(x.y - hi.y); lo.z = tf32_rna(x.z - hi.z); lo.w = tf32_rna(x.w - hi.w);
+}
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+struct Plan {
+  int U, V, Ul, Vl, vblocks, nseg, L, units, halo;   // halo = 1 for 3 taps
+};
+
+// decode unit -> strip + segment
+struct Unit { int n, ru, rv, vb, ul0, Lu; };
+__device__ __forceinline__ Unit decode_unit(int unit, const Plan& pl, int d) {
+  Unit u;
+  int t = unit;
+  const int seg = t % pl.nseg; t /= pl.nseg;
+  u.vb = t % pl.vblocks; t /= pl.vblocks;
+  u.rv = t % d; t /= d;
+  u.ru = t % d; t /= d;
+  u.n = t;
+  u.ul0 = seg * pl.L;
+  u.Lu = min(pl.L, pl.Ul - u.ul0);
+  return u;
+}
+
+template <int C>
+__global__ void __launch_bounds__(NWORK + 32, 1)
+wgrad_tc_kernel(const __grid_constant__ WgradTcArgs a, const Plan pl) {
+  using K = Cfg<C>;
+  constexpr int NST = K::NST;
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t hdr = raw + ((1024 - (raw & 1023)) & 1023);
+  unsigned char* gen = smem_raw + (hdr - raw);
+  const uint32_t bar_full = hdr, bar_empty = hdr + 8 * NST, bar_done = hdr + 16 * NST, tmem_slot = bar_done + 16;
+  const uint32_t ring = hdr + K::HDR;
+  float* bias_red = reinterpret_cast<float*>(gen + 512);   // [C] (C <= 128)
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int d = a.dil, ntaps = a.ntaps;
+  const long su = a.vert ? (long)a.W * C : C, sv = a.vert ? C : (long)a.W * C;
+
+  if (tid == 0) {
+    for (int i = 0; i < NST; ++i) { mbar_init(bar_full + 8 * i, NWORK / 2); mbar_init(bar_empty + 8 * i, 1); }
+    mbar_init(bar_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid < C) bias_red[tid] = 0.f;
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(K::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - hdr));
+
+  if (warp == 8) {
+    // =========================================================== MMA issuer
+    if (lane == 0) {
+      // M = C (ci), N = C (co), both operands MN-major (bits 15, 16)
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(C >> 3) << 17) |
+                             ((uint32_t)(C >> 4) << 24);
+      uint32_t q = 0;         // running stage-fill counter (identical on the producer side)
+      uint32_t waited = 0;    // fills [0, waited) are known to have landed
+      uint32_t started = 0;   // bit t set once accumulator t holds data
+      for (int unit = blockIdx.x; unit < pl.units; unit += gridDim.x) {
+        const Unit un = decode_unit(unit, pl, d);
+        const uint32_t q0 = q;
+        // chunk c (c = -halo .. Lu-1+halo) is fill q0 + c + halo
+        for (int j = 0; j < un.Lu; ++j) {
+          const uint32_t need = q0 + j + 2 * pl.halo + 1;   // fills up to chunk j+halo
+          while (waited < need) {
+            mbar_wait(bar_full + 8 * (waited % NST), (waited / NST) & 1);
+            ++waited;
+          }
+          tc_fence_after();
+          const uint32_t fg = q0 + j + pl.halo;             // fill holding gradient chunk j (and activation chunk j)
+          const uint32_t gbase = ring + (fg % NST) * K::STAGE + 2 * K::PART;
+          for (int t = 0; t < ntaps; ++t) {
+            const uint32_t fa = fg + t - pl.halo;           // activation chunk j + t - 1 (or j for the 1x1)
+            const uint32_t abase = ring + (fa % NST) * K::STAGE;
+#pragma unroll
+            for (int ks = 0; ks < TP / 8; ++ks) {
+              const uint64_t ah = desc_mn(abase + ks * 1024, K::SLAB), al = desc_mn(abase + K::PART + ks * 1024, K::SLAB);
+              const uint64_t gh = desc_mn(gbase + ks * 1024, K::SLAB), gl = desc_mn(gbase + K::PART + ks * 1024, K::SLAB);
+              const uint32_t acc = tmem + t * C;
+              mma_tf32(acc, ah, gh, idesc, (started >> t) & 1u);
+              started |= 1u << t;
+              mma_tf32(acc, al, gh, idesc, 1u);
+              mma_tf32(acc, ah, gl, idesc, 1u);
+            }
+          }
+          // the oldest activation chunk (j-1, or j itself for the 1x1) is no longer needed once these retire
+          umma_commit(bar_empty + 8 * ((q0 + j) % NST));
+        }
+        if (pl.halo) {   // the last two fills of the unit (chunks Lu-1 and Lu)
+          umma_commit(bar_empty + 8 * ((q0 + un.Lu) % NST));
+          umma_commit(bar_empty + 8 * ((q0 + un.Lu + 1) % NST));
+        }
+        q = q0 + un.Lu + 2 * pl.halo;
+      }
+      umma_commit(bar_done);
+    }
+  } else {
+    // =========================================================== producers: two groups fill alternate stages
+    const int grp = warp & 1;
+    const int tg = (warp >> 1) * 32 + lane;          // 0..127 inside the group
+    constexpr int C4 = C / 4;
+    constexpr int RPT = TP * C4 / 128;               // rows (float4 per part) handled by one thread: 4 (C=128) / 2 (C=64)
+    const int c4 = tg % C4, row0 = tg / C4;
+    constexpr int RSTEP = 128 / C4;                   // row stride between a thread's rows
+    const int ch = c4 * 4;
+    const uint32_t in_slab = (uint32_t)(c4 >> 3) * K::SLAB;          // 32-channel slab
+    const uint32_t c8 = (uint32_t)((c4 & 7) >> 1), halfo = (uint32_t)(c4 & 1) * 16;   // 32-byte chunk, 16-byte half
+    float4 sc = make4(1.f), sh = make4(0.f);
+    if (a.a_scale != nullptr) { sc = ldg4(a.a_scale + ch); sh = ldg4(a.a_shift + ch); }
+    float4 bsum = make4(0.f);
+    uint32_t q = 0;
+    for (int unit = blockIdx.x; unit < pl.units; unit += gridDim.x) {
+      const Unit un = decode_unit(unit, pl, d);
+      const size_t img = (size_t)un.n * a.H * a.W * C;
+      const int nfill = un.Lu + 2 * pl.halo;
+      for (int f = 0; f < nfill; ++f, ++q) {
+        if ((int)(q & 1) != grp) continue;
+        const int cidx = f - pl.halo;                          // chunk index: -1 .. Lu
+        const bool interior = cidx >= 0 && cidx < un.Lu;       // carries a gradient chunk
+        const int ul = un.ul0 + cidx;
+        const int u = un.ru + d * ul;
+        const bool uok = ul >= 0 && u < pl.U;
+        float4 av[RPT], gv[RPT];
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+          const int row = row0 + i * RSTEP;
+          const int v = un.rv + d * (un.vb * TP + row);
+          av[i] = make4(0.f);
+          gv[i] = make4(0.f);
+          if (uok && v < pl.V) {
+            const size_t off = img + u * su + v * sv + ch;
+            av[i] = ldg4(a.A + off);
+            if (a.a_scale != nullptr) {
+              av[i].x = fmaxf(fmaf(av[i].x, sc.x, sh.x), 0.f);
+              av[i].y = fmaxf(fmaf(av[i].y, sc.y, sh.y), 0.f);
+              av[i].z = fmaxf(fmaf(av[i].z, sc.z, sh.z), 0.f);
+              av[i].w = fmaxf(fmaf(av[i].w, sc.w, sh.w), 0.f);
+            }
+            if (interior) gv[i] = ldg4(a.G + off);
+          }
+        }
+        if (q >= (uint32_t)NST) mbar_wait(bar_empty + 8 * (q % NST), ((q / NST) - 1) & 1);   // ring slot free?
+        const uint32_t sbase = ring + (q % NST) * K::STAGE + in_slab;
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+          const int row = row0 + i * RSTEP;
+          const uint32_t ra = sbase + (uint32_t)row * 128;
+          const uint32_t ad = ra + (((c8 ^ ((ra >> 7) & 3)) << 5) | halfo);
+          float4 hi, lo;
+          split4(av[i], hi, lo);
+          *reinterpret_cast<float4*>(gen + (ad - hdr)) = hi;
+          *reinterpret_cast<float4*>(gen + (ad - hdr) + K::PART) = lo;
+          split4(gv[i], hi, lo);
+          *reinterpret_cast<float4*>(gen + (ad - hdr) + 2 * K::PART) = hi;
+          *reinterpret_cast<float4*>(gen + (ad - hdr) + 3 * K::PART) = lo;
+          bsum.x += gv[i].x; bsum.y += gv[i].y; bsum.z += gv[i].z; bsum.w += gv[i].w;
+        }
+        fence_proxy_async();
+        mbar_arrive(bar_full + 8 * (q % NST));
+      }
+    }
+    if (a.db != nullptr) {
+      atomicAdd(bias_red + ch + 0, bsum.x);
+      atomicAdd(bias_red + ch + 1, bsum.y);
+      atomicAdd(bias_red + ch + 2, bsum.z);
+      atomicAdd(bias_red + ch + 3, bsum.w);
+    }
+    // =========================================================== epilogue: TMEM -> red.global.add.v4
+    mbar_wait(bar_done, 0);
+    tc_fence_after();
+    __syncwarp();
+    const int qd = warp & 3, half = warp >> 2;
+    const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
+    // accumulator row (ci) held by this lane: M = 128 -> lane = row; M = 64 -> lanes 0..15 of each quarter hold rows 16q..16q+15
+    const int row = C == 128 ? qd * 32 + lane : qd * 16 + lane;
+    const bool row_ok = C == 128 ? true : lane < 16;
+    for (int t = 0; t < ntaps; ++t) {
+#pragma unroll 1
+      for (int cc = 0; cc < C / 64; ++cc) {
+        const int col0 = half * (C / 2) + cc * 32;
+        float val[32];
+        tmem_ld32(tmem + lane_addr + t * C + col0, val);
+        if (row_ok) {
+          float* dst = a.dWacc + ((size_t)t * C + row) * C + col0;
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) red_add_v4(dst + j4 * 4, val[j4 * 4 + 0], val[j4 * 4 + 1], val[j4 * 4 + 2], val[j4 * 4 + 3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (a.db != nullptr && tid < C) atomicAdd(a.db + tid, bias_red[tid]);
+  if (warp == 8) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(K::TMEM_COLS) : "memory");
+  }
+}
+
+__global__ void wgrad_unpack_kernel(const float* __restrict__ acc, float* __restrict__ dW, int C, int ntaps, long s_ci,
+                                    long s_co, long s_t) {
+  const long total = (long)ntaps * C * C;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % C);
+    const int ci = (int)((i / C) % C);
+    const int t = (int)(i / ((long)C * C));
+    dW[ci * s_ci + co * s_co + t * s_t] = acc[i];
+  }
+}
+
+template <int C>
+int launch_c(const WgradTcArgs& a, cudaStream_t s) {
+  using K = Cfg<C>;
+  static_assert(K::SMEM <= 227 * 1024, "wgrad_tc shared memory budget");
+  Plan pl;
+  pl.U = a.vert ? a.H : a.W;
+  pl.V = a.vert ? a.W : a.H;
+  pl.Ul = cdiv(pl.U, a.dil);
+  pl.Vl = cdiv(pl.V, a.dil);
+  pl.vblocks = cdiv(pl.Vl, TP);
+  pl.halo = a.ntaps == 3 ? 1 : 0;
+  const long strips = (long)a.N * a.dil * a.dil * pl.vblocks;
+  const int want = 2 * kNumSMs;
+  int nseg = (int)((want + strips - 1) / strips);
+  if (nseg < 1) nseg = 1;
+  int L = cdiv(pl.Ul, nseg);
+  if (L < 4) L = pl.Ul < 4 ? pl.Ul : 4;
+  pl.L = L;
+  pl.nseg = cdiv(pl.Ul, L);
+  const long units = strips * pl.nseg;
+  MDIL_REQUIRE(units > 0 && units < (1L << 30), "wgrad_tc: unit count");
+  pl.units = (int)units;
+  const int grid = (int)(units < kNumSMs ? units : kNumSMs);
+  MDIL_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM));
+  wgrad_tc_kernel<C><<<grid, NWORK + 32, K::SMEM, s>>>(a, pl);
+  MDIL_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace wtc
+
+int launch_wgrad_tc(const WgradTcArgs& a, cudaStream_t s) {
+  MDIL_REQUIRE(a.ntaps == 1 || a.ntaps == 3, "wgrad_tc: 1 or 3 taps");
+  MDIL_REQUIRE(a.dWacc != nullptr && ((uintptr_t)a.dWacc & 15) == 0, "wgrad_tc: accumulator buffer");
+  switch (a.C) {
+    case 128: return wtc::launch_c<128>(a, s);
+    case 64: return wtc::launch_c<64>(a, s);
+    default: return set_error(-2, "wgrad_tc: C must be 64 or 128", __FILE__, __LINE__);
+  }
+}
+
+int launch_wgrad_unpack(const float* acc, float* dW, int C, int ntaps, long s_ci, long s_co, long s_t, cudaStream_t s) {
+  const long total = (long)ntaps * C * C;
+  int grid = (int)((total + 255) / 256);
+  if (grid > kNumSMs * 4) grid = kNumSMs * 4;
+  wtc::wgrad_unpack_kernel<<<grid, 256, 0, s>>>(acc, dW, C, ntaps, s_ci, s_co, s_t);
+  MDIL_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace mdil

@@ -75,7 +75,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert sorted(set(_lib.EXPORTS)) == declared
     lib = _lib.lib()
     assert b"sm_100a" in lib.mdil_version()
-    assert lib.mdil_nb1d_packed_floats(128) == 28 * 128 * 128
+    assert lib.mdil_nb1d_packed_floats(128) == 84 * 128 * 128
 
 
 def test_missing_library_fails_loudly(monkeypatch):

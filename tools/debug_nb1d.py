@@ -16,6 +16,9 @@ def run(C, dil, rap, N, H, W, pdrop):
     mod = M.non_bottleneck_1d_RAP(C, pdrop, dil, 2) if rap else M.non_bottleneck_1d(C, pdrop, dil)
     _randomize(mod, 3)
     sd = {k: v.detach().clone() for k, v in mod.state_dict().items()}
+    for k, v in sd.items():
+        if v.dtype.is_floating_point and "running" not in k:
+            v.requires_grad_(True)
     mod = mod.cuda().train()
     g = torch.Generator().manual_seed(5)
     x = torch.relu(torch.randn(N, C, H, W, generator=g)); dy = torch.randn(N, C, H, W, generator=g)
@@ -60,6 +63,9 @@ def run(C, dil, rap, N, H, W, pdrop):
     stop = int(os.environ.get("MDIL_DEBUG_STOP", "0"))
     if stop == 0:
         print("bwd  dp(T1)", rel(view(o1), p.grad), " da'(T2)", rel(view(o2), a.grad * (a > 0)), " dq(T3)", rel(view(o3), q.grad), " dx", rel(xd.grad, xo.grad))
+        for (nm, prm) in mod.named_parameters():
+            if prm.grad is not None and nm in sd and sd[nm].grad is not None:
+                print(f"     d{nm:28s} {rel(prm.grad, sd[nm].grad):.3e}   (max ref {float(sd[nm].grad.abs().max()):.3e})")
     else:
         print(f"bwd stop={stop} ds(T1)", rel(view(o1), s.grad), " dc'(T2)", rel(view(o2), c.grad * (c > 0)), " dq(T3)", rel(view(o3), q.grad))
         d = (view(o1).cpu() - s.grad).abs()
@@ -75,4 +81,6 @@ def run(C, dil, rap, N, H, W, pdrop):
     return
 
 if __name__ == "__main__":
-    run(128, 1, True, 2, 64, 128, 0.0)
+    import itertools
+    for cfg in [(128, 16, True, 2, 4, 8, 0.0), (128, 2, True, 2, 4, 8, 0.0), (64, 1, True, 2, 8, 16, 0.0), (128, 4, True, 2, 16, 32, 0.0), (64, 1, False, 2, 8, 16, 0.0)]:
+        run(*cfg)

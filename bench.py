@@ -128,8 +128,11 @@ def oracle_step_factory(workload, n):
 
 
 def time_cpu(workload, n, steps, warmup):
-    import torch
     cores = os.cpu_count() or 1
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host thread (set before torch spins up its pool)
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    os.environ["MKL_NUM_THREADS"] = str(cores)
+    import torch
     torch.set_num_threads(cores)
     step = oracle_step_factory(workload, n)
     for _ in range(warmup):
@@ -298,7 +301,7 @@ def run_ours(args):
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                         "h2d_bytes_per_step": images_h.numel() * 4 + labels_h.numel() * 8, "d2h_bytes_per_step": 4},
                 "gpu_launches": int(launches), "roofline": roofline}
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:   # CPU baseline: rank 0 at N=1 only
             cpu_steps = 2 if args.workload == "step1" else 1
             v, ms, cores = time_cpu(args.workload, 1, cpu_steps, 1)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",

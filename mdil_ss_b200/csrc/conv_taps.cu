@@ -29,10 +29,11 @@ conv_taps_kernel(const __grid_constant__ ConvGeom g, const float* __restrict__ A
   const bool lvalid = lp < P;
   int ln = 0, lvy = 0, lvx = 0;
   if (lvalid) {
-    lvx = (int)(lp % g.VW);
-    size_t t = lp / g.VW;
-    lvy = (int)(t % g.VH);
-    ln = (int)(t / g.VH);
+    const unsigned lq32 = (unsigned)lp;
+    lvx = (int)(lq32 % (unsigned)g.VW);
+    const unsigned t = lq32 / (unsigned)g.VW;
+    lvy = (int)(t % (unsigned)g.VH);
+    ln = (int)(t / (unsigned)g.VH);
   }
   const int n0 = blockIdx.y * CT_N;
   const int brow = tid >> 4, bcol = (tid & 15) * 4;
@@ -98,10 +99,11 @@ conv_taps_kernel(const __grid_constant__ ConvGeom g, const float* __restrict__ A
   for (int i = 0; i < 8; ++i) {
     const size_t p = (size_t)blockIdx.x * CT_M + tm * 8 + i;
     if (p >= P) continue;
-    const int vx = (int)(p % g.VW);
-    const size_t tt = p / g.VW;
-    const int vy = (int)(tt % g.VH);
-    const int n = (int)(tt / g.VH);
+    const unsigned p32 = (unsigned)p;
+    const int vx = (int)(p32 % (unsigned)g.VW);
+    const unsigned tt = p32 / (unsigned)g.VW;
+    const int vy = (int)(tt % (unsigned)g.VH);
+    const int n = (int)(tt / (unsigned)g.VH);
     const int oy = vy * g.g_sy + tc.o_dy, ox = vx * g.g_sx + tc.o_dx;
     if (oy < 0 || oy >= g.GH || ox < 0 || ox >= g.GW) continue;
     float* o = out + (((size_t)n * g.GH + oy) * g.GW + ox) * g.ldg + g.g_coff + co;
@@ -116,6 +118,7 @@ conv_taps_kernel(const __grid_constant__ ConvGeom g, const float* __restrict__ A
 }
 
 int launch_conv_taps(const ConvGeom& g, const float* A, const float* Wp, const float* bias, float* out, cudaStream_t s) {
+  MDIL_REQUIRE((size_t)g.N * g.VH * g.VW < (1ull << 31), "conv_taps: more than 2^31 pixels");
   MDIL_REQUIRE(g.CIN % 4 == 0 && g.lda % 4 == 0 && g.a_coff % 4 == 0 && g.COUT_PAD % 4 == 0, "conv_taps: alignment");
   MDIL_REQUIRE(g.nclasses >= 1 && g.nclasses <= kMaxClasses, "conv_taps: classes");
   size_t P = (size_t)g.N * g.VH * g.VW;
@@ -177,14 +180,14 @@ wgrad_taps_kernel(const __grid_constant__ ConvGeom g, const float* __restrict__ 
   for (size_t p0 = p_begin; p0 < p_end; p0 += KP) {
     for (int idx = tid; idx < KP * (CI_TILE / 4); idx += 256) {
       const int kp = idx / (CI_TILE / 4), f4 = idx % (CI_TILE / 4);
-      const size_t p = p0 + kp;
+      const unsigned p = (unsigned)p0 + kp;
       const int ci = ci0 + f4 * 4;
       float4 v = make4(0.f);
-      if (p < p_end && ci < g.CIN) {
-        const int vx = (int)(p % g.VW);
-        const size_t tt = p / g.VW;
-        const int vy = (int)(tt % g.VH);
-        const int n = (int)(tt / g.VH);
+      if (p < (unsigned)p_end && ci < g.CIN) {
+        const int vx = (int)(p % (unsigned)g.VW);
+        const unsigned tt = p / (unsigned)g.VW;
+        const int vy = (int)(tt % (unsigned)g.VH);
+        const int n = (int)(tt / (unsigned)g.VH);
         const int ay = vy * g.a_sy + tc.a_dy[t], ax = vx * g.a_sx + tc.a_dx[t];
         if (ay >= 0 && ay < g.AH && ax >= 0 && ax < g.AW) {
           v = ldg4(A + (((size_t)n * g.AH + ay) * g.AW + ax) * g.lda + g.a_coff + ci);
@@ -201,14 +204,14 @@ wgrad_taps_kernel(const __grid_constant__ ConvGeom g, const float* __restrict__ 
     }
     for (int idx = tid; idx < KP * (CO_TILE / 4); idx += 256) {
       const int kp = idx / (CO_TILE / 4), f4 = idx % (CO_TILE / 4);
-      const size_t p = p0 + kp;
+      const unsigned p = (unsigned)p0 + kp;
       const int co = co0 + f4 * 4;
       float4 v = make4(0.f);
-      if (p < p_end && co < g.COUT) {
-        const int vx = (int)(p % g.VW);
-        const size_t tt = p / g.VW;
-        const int vy = (int)(tt % g.VH);
-        const int n = (int)(tt / g.VH);
+      if (p < (unsigned)p_end && co < g.COUT) {
+        const int vx = (int)(p % (unsigned)g.VW);
+        const unsigned tt = p / (unsigned)g.VW;
+        const int vy = (int)(tt % (unsigned)g.VH);
+        const int n = (int)(tt / (unsigned)g.VH);
         const int gy = vy * g.g_sy + tc.o_dy, gx = vx * g.g_sx + tc.o_dx;
         if (gy >= 0 && gy < g.GH && gx >= 0 && gx < g.GW)
           v = ldg4(G + (((size_t)n * g.GH + gy) * g.GW + gx) * g.ldg + g.g_coff + co);
@@ -273,10 +276,131 @@ static int wgrad_launch(const ConvGeom& g, const float* A, const float* a_scale,
   return 0;
 }
 
+// ---- small-channel weight gradient (CIN <= 16, COUT <= 16: the C = 16 decoder blocks and the 3->13 initial conv).
+// HBM/L1-bound: 16 threads share a pixel (4x4 register tiles over ci x co), 16 pixel lanes per CTA, up to 3 taps per
+// pass; operands come straight from global memory (the 64-byte pixel rows are L1-resident across the 16 threads).
+template <int NT>
+__global__ void __launch_bounds__(256, 3)
+wgrad_small_kernel(const __grid_constant__ ConvGeom g, const float* __restrict__ A, const float* __restrict__ a_scale,
+                   const float* __restrict__ a_shift, const float* __restrict__ G, float* __restrict__ dW, long s_ci,
+                   long s_co, long s_t, float* __restrict__ db, int pixels_per_cta) {
+  __shared__ float red[8][16][NT * 16 + 4];
+  const TapClass& tc = g.cls[0];
+  const int tid = threadIdx.x, tile = tid & 15, pl = tid >> 4;
+  const int ci0 = (tile >> 2) * 4, co0 = (tile & 3) * 4;
+  const int tap0 = blockIdx.y * NT;
+  const size_t P = (size_t)g.N * g.VH * g.VW;
+  const size_t p_begin = (size_t)blockIdx.x * pixels_per_cta;
+  const size_t p_end = p_begin + pixels_per_cta < P ? p_begin + pixels_per_cta : P;
+  const bool ci_ok = ci0 < g.CIN, co_ok = co0 < g.COUT;
+  float4 sc = make4(1.f), sh = make4(0.f);
+  if (a_scale != nullptr && ci_ok) { sc = ldg4(a_scale + ci0); sh = ldg4(a_shift + ci0); }
+  float acc[NT][4][4];
+#pragma unroll
+  for (int t = 0; t < NT; ++t)
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[t][i][j] = 0.f;
+  float4 bsum = make4(0.f);
+  // running (n, vy, vx) of this thread's pixel: one division at entry, increments afterwards (32-bit: P < 2^31)
+  unsigned p = (unsigned)p_begin + pl;
+  int vx = (int)(p % (unsigned)g.VW);
+  int vy = (int)((p / (unsigned)g.VW) % (unsigned)g.VH);
+  int n = (int)(p / ((unsigned)g.VW * (unsigned)g.VH));
+  const float* Gc = G + g.g_coff + co0;
+  const float* Ac = A + g.a_coff + ci0;
+  for (; p < (unsigned)p_end; p += 16) {
+    const int gy = vy * g.g_sy + tc.o_dy, gx = vx * g.g_sx + tc.o_dx;
+    float4 gv = make4(0.f);
+    if (co_ok && (unsigned)gy < (unsigned)g.GH && (unsigned)gx < (unsigned)g.GW)
+      gv = ldg4(Gc + (size_t)((unsigned)(n * g.GH + gy) * (unsigned)g.GW + (unsigned)gx) * (unsigned)g.ldg);
+    bsum.x += gv.x; bsum.y += gv.y; bsum.z += gv.z; bsum.w += gv.w;
+    const float gg[4] = {gv.x, gv.y, gv.z, gv.w};
+    const int ayb = vy * g.a_sy, axb = vx * g.a_sx;
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      const int tap = tap0 + t;
+      if (tap < tc.ntaps) {
+        const int ay = ayb + tc.a_dy[tap], ax = axb + tc.a_dx[tap];
+        float4 av = make4(0.f);
+        if (ci_ok && (unsigned)ay < (unsigned)g.AH && (unsigned)ax < (unsigned)g.AW) {
+          av = ldg4(Ac + (size_t)((unsigned)(n * g.AH + ay) * (unsigned)g.AW + (unsigned)ax) * (unsigned)g.lda);
+          if (a_scale != nullptr) {
+            av.x = fmaxf(fmaf(av.x, sc.x, sh.x), 0.f); av.y = fmaxf(fmaf(av.y, sc.y, sh.y), 0.f);
+            av.z = fmaxf(fmaf(av.z, sc.z, sh.z), 0.f); av.w = fmaxf(fmaf(av.w, sc.w, sh.w), 0.f);
+          }
+        }
+        const float aa[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[t][i][j] = fmaf(aa[i], gg[j], acc[t][i][j]);
+      }
+    }
+    vx += 16;
+    while (vx >= g.VW) { vx -= g.VW; ++vy; }
+    while (vy >= g.VH) { vy -= g.VH; ++n; }
+  }
+  // reduce over the 16 pixel lanes: lanes l and l^16 of a warp share a tile, then across the 8 warps through smem
+  const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+  for (int t = 0; t < NT; ++t)
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float v = acc[t][i][j];
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        if (lane < 16) red[warp][tile][t * 16 + i * 4 + j] = v;
+      }
+  float bs[4] = {bsum.x, bsum.y, bsum.z, bsum.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    bs[j] += __shfl_xor_sync(0xffffffffu, bs[j], 16);
+    if (lane < 16) red[warp][tile][NT * 16 + j] = bs[j];
+  }
+  __syncthreads();
+  for (int e = tid; e < 16 * (NT * 16 + 4); e += 256) {
+    const int tl = e / (NT * 16 + 4), k = e % (NT * 16 + 4);
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += red[w][tl][k];
+    const int ci_b = (tl >> 2) * 4, co_b = (tl & 3) * 4;
+    if (k < NT * 16) {
+      const int t = k / 16, i = (k % 16) / 4, j = k % 4;
+      const int tap = tap0 + t, ci = ci_b + i, co = co_b + j;
+      if (tap < tc.ntaps && ci < g.CIN_VALID && co < g.COUT)
+        atomicAdd(dW + (long)tc.widx[tap] * s_t + (long)ci * s_ci + (long)co * s_co, v);
+    } else if (db != nullptr && blockIdx.y == 0 && ci_b == 0) {
+      const int co = co_b + (k - NT * 16);
+      if (co < g.COUT) atomicAdd(db + co, v);
+    }
+  }
+}
+
+static int wgrad_small_launch(const ConvGeom& g, const float* A, const float* a_scale, const float* a_shift, const float* G,
+                              float* dW, long s_ci, long s_co, long s_t, float* db, cudaStream_t s) {
+  const int ntaps = g.cls[0].ntaps;
+  const int passes = cdiv(ntaps, 3);
+  size_t P = (size_t)g.N * g.VH * g.VW;
+  int want = cdiv(4 * kNumSMs, passes);
+  size_t ppc = (P + want - 1) / want;
+  ppc = (ppc + 15) / 16 * 16;
+  if (ppc < 16) ppc = 16;
+  dim3 grid((unsigned)((P + ppc - 1) / ppc), (unsigned)passes);
+  wgrad_small_kernel<3><<<grid, 256, 0, s>>>(g, A, a_scale, a_shift, G, dW, s_ci, s_co, s_t, db, (int)ppc);
+  MDIL_LAUNCH_CHECK();
+  return 0;
+}
+
 int launch_wgrad_taps(const ConvGeom& g, const float* A, const float* a_scale, const float* a_shift, const float* G,
                       float* dW, long s_ci, long s_co, long s_t, float* db, cudaStream_t s) {
   MDIL_REQUIRE(g.CIN % 4 == 0 && g.lda % 4 == 0 && g.a_coff % 4 == 0 && g.ldg % 4 == 0 && g.g_coff % 4 == 0,
                "wgrad_taps: alignment");
+  MDIL_REQUIRE((size_t)g.N * g.VH * g.VW < (1ull << 31), "wgrad_taps: more than 2^31 pixels");
+  if (g.CIN <= 16 && g.COUT <= 16 && g.nclasses == 1)
+    return wgrad_small_launch(g, A, a_scale, a_shift, G, dW, s_ci, s_co, s_t, db, s);
   const int tm = g.CIN >= 128 ? 8 : (g.CIN >= 64 ? 4 : 1);
   const int tn = g.COUT >= 128 ? 8 : (g.COUT > 16 ? 4 : 1);
 #define MDIL_WG(TM_, TN_, KP_) \

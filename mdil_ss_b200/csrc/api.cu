@@ -21,6 +21,16 @@ int set_error(int code, const char* what, const char* file, int line) {
   return code == 0 ? -1 : code;
 }
 
+int pair_impl_mode() {
+  static const int mode = [] {
+    const char* e = getenv("MDIL_PAIR_IMPL");
+    if (e != nullptr && strcmp(e, "ffma") == 0) return 0;
+    if (e != nullptr && strcmp(e, "tc2") == 0) return 2;
+    return 3;
+  }();
+  return mode;
+}
+
 namespace {
 
 inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
@@ -128,13 +138,7 @@ int mdil_nchw_to_nhwc4(const float* x, float* y, int N, int C, int H, int W, voi
 // [0, 28 C^2): fp32 streams of the FFMA kernel; [28 C^2, 84 C^2): hi/lo images of the tensor-core kernel (4 x 14 C^2)
 size_t mdil_nb1d_packed_floats(int C) { return (size_t)84 * C * C; }
 
-static bool use_tensor_cores(int C) {
-  static const int mode = [] {
-    const char* e = getenv("MDIL_PAIR_IMPL");
-    return (e != nullptr && strcmp(e, "ffma") == 0) ? 0 : 1;
-  }();
-  return mode == 1 && (C == 64 || C == 128);
-}
+static bool use_tensor_cores(int C) { return pair_impl_mode() != 0 && (C == 64 || C == 128); }
 static bool use_tc_wgrad(int C) {
   static const int mode = [] {
     const char* e = getenv("MDIL_WGRAD_IMPL");
@@ -177,9 +181,12 @@ int mdil_nb1d_pack(const mdil_nb1d_desc* d, const mdil_nb1d_weights* w, float* p
     MDIL_TRY(launch_pack(w->wp1, packed + 27 * CC, 1, C, C, C, C, C, 1, 0, 0, s));
   }
   if (use_tensor_cores(C)) {
-    for (int which = 0; which < 4; ++which)
-      MDIL_TRY(launch_pack_tc(packed + (size_t)which * 7 * CC, packed + 28 * CC + (size_t)which * 14 * CC, C,
-                              d->has_adapter, s));
+    for (int which = 0; which < 4; ++which) {
+      const float* src = packed + (size_t)which * 7 * CC;
+      float* dst = packed + 28 * CC + (size_t)which * 14 * CC;
+      MDIL_TRY(pair_impl_mode() == 3 ? launch_pack_tc3(src, dst, C, d->has_adapter, s)
+                                     : launch_pack_tc(src, dst, C, d->has_adapter, s));
+    }
   }
   return 0;
 }

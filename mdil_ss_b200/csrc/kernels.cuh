@@ -106,6 +106,9 @@ int launch_pair(const PairArgs& a, cudaStream_t s);          // dispatch: tensor
 int launch_pair_ffma(const PairArgs& a, cudaStream_t s);     // nb1d_pair.cu (FP32 FFMA; all C)
 int launch_pair_tc(const PairArgs& a, cudaStream_t s);       // nb1d_pair_tc.cu (tcgen05 3xTF32; C = 64, 128)
 int launch_pack_tc(const float* src_stream, float* dst_stream, int C, int has_adapter, cudaStream_t s);
+int launch_pair_tc3(const PairArgs& a, cudaStream_t s);      // nb1d_pair_tc3.cu (persistent pipelined tcgen05 kernel; default)
+int launch_pack_tc3(const float* src_stream, float* dst_stream, int C, int has_adapter, cudaStream_t s);
+int pair_impl_mode();   // MDIL_PAIR_IMPL: 0 = "ffma", 2 = "tc2" (one tile per CTA), 3 = pipelined tensor-core kernel (default)
 void pair_profile_record_begin(const PairArgs& a, cudaStream_t s, void** rec);
 void pair_profile_record_end(cudaStream_t s, void* rec);
 int pair_profile_begin();

@@ -477,7 +477,8 @@ int launch_pair(const PairArgs& a_in, cudaStream_t s) {
   a.trace = trace;
   void* rec = nullptr;
   pair_profile_record_begin(a, s, &rec);
-  const int rc = (a.wstream_tc != nullptr && (a.C == 64 || a.C == 128)) ? launch_pair_tc(a, s) : launch_pair_ffma(a, s);
+  const bool tc = a.wstream_tc != nullptr && (a.C == 64 || a.C == 128);
+  const int rc = !tc ? launch_pair_ffma(a, s) : (pair_impl_mode() == 3 ? launch_pair_tc3(a, s) : launch_pair_tc(a, s));
   pair_profile_record_end(s, rec);
   return rc;
 }

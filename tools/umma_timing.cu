@@ -81,7 +81,7 @@ __global__ void timing(const float* wsrc, long long* out, int N) {
 int main() {
   float* w; long long* out; long long h[64];
   CK(cudaMalloc(&w, 1 << 20)); CK(cudaMemset(w, 0, 1 << 20)); CK(cudaMalloc(&out, 64 * 8));
-  for (int N : {128, 64}) {
+  for (int N : {256, 192, 128, 64, 32, 16}) {
     CK(cudaMemset(out, 0, 64 * 8));
     CK(cudaFuncSetAttribute(timing, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     timing<<<1, 128, 200 * 1024>>>(w, out, N);

@@ -48,7 +48,13 @@ template <int C> struct Cfg {
   static constexpr uint32_t SMEM_BYTES = 1024 + HDR_BYTES + NBUF * BUF_BYTES + NSTAGE * STAGE_BYTES + STG_BYTES;
   static constexpr int NCH = C / KC;
   static constexpr int NSB = C / 32;                         // 16-column sub-blocks per epilogue warp
-  static constexpr uint32_t TMEM_COLS = C == 64 ? 256 : 512; // acc1 [C] + acc2 [2][C], power of two
+  // C = 64: the hi and lo weight images of a chunk are stacked along N (one MMA with N = 2C computes x*Whi into columns
+  // [0,C) and x*Wlo into [C,2C)): 4 MMAs per chunk instead of 6 (the issue rate of the single MMA thread, ~100 clocks
+  // per instruction whatever N <= 128, is what bounds the tensor pipe here: tools/umma_issue*.cu); the epilogues add the
+  // two column halves.  C = 128 would need N = 256 accumulators (768 TMEM columns with the double buffer): not stacked.
+  static constexpr bool NSTACK = C == 64;
+  static constexpr uint32_t ACCW = NSTACK ? 2 * C : C;       // accumulator width in TMEM columns
+  static constexpr uint32_t TMEM_COLS = 512;                 // acc1 [ACCW] + acc2 [2][ACCW] = 384 columns, power of two
 };
 
 struct TileShape { int TU, TV, TR; };
@@ -113,6 +119,25 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// sum of two 16-column accumulator pieces (both loads in flight, one wait)
+__device__ __forceinline__ void tmem_ld16x2(uint32_t ta, uint32_t tb, float (&v)[16]) {
+  uint32_t r[16], q[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(ta));
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]), "=r"(q[8]),
+        "=r"(q[9]), "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15])
+      : "r"(tb));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + __uint_as_float(q[i]);
 }
 __device__ __forceinline__ float tf32_rna(float x) {
   uint32_t r;
@@ -277,7 +302,7 @@ pair_tc3_kernel(const __grid_constant__ PairArgs a, const Geo geo) {
     }
   } else if (warp == W_MMA) {
     // ============================================================ MMA issuer (whole warp walks the loop, lane 0 issues)
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(C >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(K::ACCW >> 3) << 17) | ((128u >> 4) << 24);
     const uint32_t a_hiw = (1024u >> 4) | (1u << 14) | (2u << 29);
     const uint32_t b_hiw = (512u >> 4) | (1u << 14) | (4u << 29);
     const uint32_t ring0 = ((ring & 0x3FFFF) >> 4) | (1u << 16);
@@ -293,12 +318,19 @@ pair_tc3_kernel(const __grid_constant__ PairArgs a, const Geo geo) {
       const uint32_t ah = ahi0 + ad, al = alo0 + ad;
       const uint32_t bh = ring0 + st * (K::STAGE_BYTES >> 4), bl = bh + (K::HALF_STAGE >> 4);
       if (lane == 0) {
-        mma_tf32_w(acc, ah, a_hiw, bh, b_hiw, idesc, accumulate);
-        mma_tf32_w(acc, al, a_hiw, bh, b_hiw, idesc, 1u);
-        mma_tf32_w(acc, ah, a_hiw, bl, b_hiw, idesc, 1u);
-        mma_tf32_w(acc, ah + 2, a_hiw, bh + 2, b_hiw, idesc, 1u);     // second K step: +32 bytes
-        mma_tf32_w(acc, al + 2, a_hiw, bh + 2, b_hiw, idesc, 1u);
-        mma_tf32_w(acc, ah + 2, a_hiw, bl + 2, b_hiw, idesc, 1u);
+        if (K::NSTACK) {     // B = [W_hi ; W_lo] (2C rows: the lo image follows the hi image at the same row pitch)
+          mma_tf32_w(acc, ah, a_hiw, bh, b_hiw, idesc, accumulate);
+          mma_tf32_w(acc, ah + 2, a_hiw, bh + 2, b_hiw, idesc, 1u);   // second K step: +32 bytes
+          mma_tf32_w(acc, al, a_hiw, bh, b_hiw, idesc, 1u);
+          mma_tf32_w(acc, al + 2, a_hiw, bh + 2, b_hiw, idesc, 1u);
+        } else {
+          mma_tf32_w(acc, ah, a_hiw, bh, b_hiw, idesc, accumulate);
+          mma_tf32_w(acc, al, a_hiw, bh, b_hiw, idesc, 1u);
+          mma_tf32_w(acc, ah, a_hiw, bl, b_hiw, idesc, 1u);
+          mma_tf32_w(acc, ah + 2, a_hiw, bh + 2, b_hiw, idesc, 1u);
+          mma_tf32_w(acc, al + 2, a_hiw, bh + 2, b_hiw, idesc, 1u);
+          mma_tf32_w(acc, ah + 2, a_hiw, bl + 2, b_hiw, idesc, 1u);
+        }
         if (CL > 1) umma_commit_mc(bar_wempty + 8 * st, cl_mask);       // ring slot reusable when these retire
         else umma_commit(bar_wempty + 8 * st);
       }
@@ -310,7 +342,7 @@ pair_tc3_kernel(const __grid_constant__ PairArgs a, const Geo geo) {
       const uint32_t act_hi = act0 + (uint32_t)b * K::BUF_BYTES, act_lo = act_hi + K::ACT_BYTES;
       ahi0 = ((act_hi & 0x3FFFF) >> 4) | (1u << 16);
       alo0 = ((act_lo & 0x3FFFF) >> 4) | (1u << 16);
-      const uint32_t acc2 = tmem + C + (uint32_t)a2 * C;
+      const uint32_t acc2 = tmem + K::ACCW + (uint32_t)a2 * K::ACCW;
       if (it >= 2) {   // epilogue 2 of tile it-2 has drained this accumulator
         const long long tw0 = tracing ? clock64() : 0;
         mbar_wait(bar_acc2free + 8 * a2, ((it >> 1) - 1) & 1);
@@ -445,7 +477,7 @@ pair_tc3_kernel(const __grid_constant__ PairArgs a, const Geo geo) {
       const int pix_mid = mid_valid ? (a.vert_first ? u * a.W + vm : vm * a.W + u) : -1;
       const int pix_out = out_valid ? (a.vert_first ? u * a.W + vo : vo * a.W + u) : -1;
       unsigned char* hi_base = gen + K::HDR_BYTES + (size_t)b * K::BUF_BYTES;
-      const uint32_t acc2 = tmem + C + (uint32_t)a2 * C;
+      const uint32_t acc2 = tmem + K::ACCW + (uint32_t)a2 * K::ACCW;
 
       // ================================================== epilogue 1: mid = f(acc1) -> hi/lo A operand (rows m)
       float4 pre[4], pre2[4];
@@ -483,7 +515,8 @@ pair_tc3_kernel(const __grid_constant__ PairArgs a, const Geo geo) {
           }
           if (i + 1 < K::NSB) fetch_mask(i + 1);
         }
-        tmem_ld16(acc1 + lane_addr + ch0, val);
+        if (K::NSTACK) tmem_ld16x2(acc1 + lane_addr + ch0, acc1 + lane_addr + C + ch0, val);
+        else tmem_ld16(acc1 + lane_addr + ch0, val);
         if (mid_valid) {
           if (a.mid_mask != nullptr) {
 #pragma unroll
@@ -582,7 +615,8 @@ pair_tc3_kernel(const __grid_constant__ PairArgs a, const Geo geo) {
           }
           if (i + 1 < K::NSB) fetch_epi(i + 1);
         }
-        tmem_ld16(acc2 + lane_addr + ch0, val);
+        if (K::NSTACK) tmem_ld16x2(acc2 + lane_addr + ch0, acc2 + lane_addr + C + ch0, val);
+        else tmem_ld16(acc2 + lane_addr + ch0, val);
         if (i == K::NSB - 1) {     // last read of this accumulator: the MMA warp may overwrite it (tile it+2)
           tc_fence_before();
           mbar_arrive(bar_acc2free + 8 * a2);

@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+echo "=== nb1d blocks"; timeout -s KILL 120 python -m pytest tests/test_gpu_blocks.py -q -m gpu -k "nb1d" -p no:cacheprovider -x 2>&1 | tail -4
+echo "=== trace"; MDIL_TC_TRACE=1 timeout -s KILL 60 python tools/trace_tc.py 2>&1 | grep -E "pair_tc3|Error|error" | cut -c1-420
+echo "=== net"; timeout -s KILL 120 python -m pytest tests/test_gpu_net.py -q -m gpu -p no:cacheprovider 2>&1 | tail -3
+echo "=== bench"; timeout -s KILL 120 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>gpurun_out/bench.err | tee gpurun_out/bench_tc3.json | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['roofline']['per_kind_ms_per_step'])"; tail -3 gpurun_out/bench.err | cut -c1-300

@@ -163,31 +163,14 @@ int mdil_nb1d_pack(const mdil_nb1d_desc* d, const mdil_nb1d_weights* w, float* p
   const int C = d->C;
   const long CC = (long)C * C;
   cudaStream_t s = S(stream);
-  // forward streams: slab[k][ci][co] = W[co][ci][k]
-  MDIL_TRY(launch_pack(w->w31_1, packed + 0 * CC, 3, C, C, C, C, 3, 3L * C, 1, 0, s));
-  MDIL_TRY(launch_pack(w->w13_1, packed + 3 * CC, 3, C, C, C, C, 3, 3L * C, 1, 0, s));
-  MDIL_TRY(launch_pack(w->w31_2, packed + 7 * CC, 3, C, C, C, C, 3, 3L * C, 1, 0, s));
-  MDIL_TRY(launch_pack(w->w13_2, packed + 10 * CC, 3, C, C, C, C, 3, 3L * C, 1, 0, s));
-  // backward streams (second conv first, taps flipped): slab[k'][co][ci] = W[co][ci][2-k']
-  MDIL_TRY(launch_pack(w->w13_2, packed + 14 * CC, 3, C, C, C, C, 3L * C, 3, 1, 1, s));
-  MDIL_TRY(launch_pack(w->w31_2, packed + 17 * CC, 3, C, C, C, C, 3L * C, 3, 1, 1, s));
-  MDIL_TRY(launch_pack(w->w13_1, packed + 21 * CC, 3, C, C, C, C, 3L * C, 3, 1, 1, s));
-  MDIL_TRY(launch_pack(w->w31_1, packed + 24 * CC, 3, C, C, C, C, 3L * C, 3, 1, 1, s));
-  if (d->has_adapter) {
-    MDIL_REQUIRE(w->wp1 != nullptr && w->wp2 != nullptr, "nb1d: adapter weights missing");
-    MDIL_TRY(launch_pack(w->wp1, packed + 6 * CC, 1, C, C, C, C, 1, C, 0, 0, s));    // [ci][co] = Wp[co][ci]
-    MDIL_TRY(launch_pack(w->wp2, packed + 13 * CC, 1, C, C, C, C, 1, C, 0, 0, s));
-    MDIL_TRY(launch_pack(w->wp2, packed + 20 * CC, 1, C, C, C, C, C, 1, 0, 0, s));   // [co][ci]
-    MDIL_TRY(launch_pack(w->wp1, packed + 27 * CC, 1, C, C, C, C, C, 1, 0, 0, s));
-  }
-  if (use_tensor_cores(C)) {
-    for (int which = 0; which < 4; ++which) {
-      const float* src = packed + (size_t)which * 7 * CC;
-      float* dst = packed + 28 * CC + (size_t)which * 14 * CC;
-      MDIL_TRY(pair_impl_mode() == 3 ? launch_pack_tc3(src, dst, C, d->has_adapter, s)
-                                     : launch_pack_tc(src, dst, C, d->has_adapter, s));
-    }
-  }
+  // streams (28 C^2 floats): [which][7][ci or co][co or ci], which = fwd pair 1, fwd pair 2, bwd pair 2, bwd pair 1;
+  // forward slab[k][ci][co] = W[co][ci][k], backward (second conv first, taps flipped) slab[k'][co][ci] = W[co][ci][2-k'];
+  // tensor-core images (56 C^2 floats) are written by the same launch
+  if (d->has_adapter) MDIL_REQUIRE(w->wp1 != nullptr && w->wp2 != nullptr, "nb1d: adapter weights missing");
+  const float* w6[6] = {w->w31_1, w->w13_1, w->w31_2, w->w13_2, w->wp1, w->wp2};
+  const bool tc = use_tensor_cores(C);
+  (void)CC;
+  MDIL_TRY(launch_pack_block(w6, packed, C, d->has_adapter, tc ? 0 : 1, tc ? pair_impl_mode() : 0, s));
   return 0;
 }
 

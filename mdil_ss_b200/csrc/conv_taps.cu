@@ -280,7 +280,7 @@ static int wgrad_launch(const ConvGeom& g, const float* A, const float* a_scale,
 // HBM/L1-bound: 16 threads share a pixel (4x4 register tiles over ci x co), 16 pixel lanes per CTA, up to 3 taps per
 // pass; operands come straight from global memory (the 64-byte pixel rows are L1-resident across the 16 threads).
 template <int NT>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 2)
 wgrad_small_kernel(const __grid_constant__ ConvGeom g, const float* __restrict__ A, const float* __restrict__ a_scale,
                    const float* __restrict__ a_shift, const float* __restrict__ G, float* __restrict__ dW, long s_ci,
                    long s_co, long s_t, float* __restrict__ db, int pixels_per_cta) {
@@ -303,44 +303,62 @@ wgrad_small_kernel(const __grid_constant__ ConvGeom g, const float* __restrict__
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[t][i][j] = 0.f;
   float4 bsum = make4(0.f);
-  // running (n, vy, vx) of this thread's pixel: one division at entry, increments afterwards (32-bit: P < 2^31)
+  // running (n, vy, vx) of this thread's pixel: one division at entry, increments afterwards (32-bit: P < 2^31).
+  // Software-pipelined: the loads of U pixels (U * (1 + NT) independent 128-bit loads) are issued before the first FMA.
+  constexpr int U = 4;
   unsigned p = (unsigned)p_begin + pl;
   int vx = (int)(p % (unsigned)g.VW);
   int vy = (int)((p / (unsigned)g.VW) % (unsigned)g.VH);
   int n = (int)(p / ((unsigned)g.VW * (unsigned)g.VH));
   const float* Gc = G + g.g_coff + co0;
   const float* Ac = A + g.a_coff + ci0;
-  for (; p < (unsigned)p_end; p += 16) {
-    const int gy = vy * g.g_sy + tc.o_dy, gx = vx * g.g_sx + tc.o_dx;
-    float4 gv = make4(0.f);
-    if (co_ok && (unsigned)gy < (unsigned)g.GH && (unsigned)gx < (unsigned)g.GW)
-      gv = ldg4(Gc + (size_t)((unsigned)(n * g.GH + gy) * (unsigned)g.GW + (unsigned)gx) * (unsigned)g.ldg);
-    bsum.x += gv.x; bsum.y += gv.y; bsum.z += gv.z; bsum.w += gv.w;
-    const float gg[4] = {gv.x, gv.y, gv.z, gv.w};
-    const int ayb = vy * g.a_sy, axb = vx * g.a_sx;
+  for (; p < (unsigned)p_end; p += 16 * U) {
+    float4 gv[U], av[U][NT];
+    unsigned inimg = 0;   // bit u*NT+t: the activation tap is inside the image (the BN+ReLU prologue applies)
 #pragma unroll
-    for (int t = 0; t < NT; ++t) {
-      const int tap = tap0 + t;
-      if (tap < tc.ntaps) {
-        const int ay = ayb + tc.a_dy[tap], ax = axb + tc.a_dx[tap];
-        float4 av = make4(0.f);
-        if (ci_ok && (unsigned)ay < (unsigned)g.AH && (unsigned)ax < (unsigned)g.AW) {
-          av = ldg4(Ac + (size_t)((unsigned)(n * g.AH + ay) * (unsigned)g.AW + (unsigned)ax) * (unsigned)g.lda);
-          if (a_scale != nullptr) {
-            av.x = fmaxf(fmaf(av.x, sc.x, sh.x), 0.f); av.y = fmaxf(fmaf(av.y, sc.y, sh.y), 0.f);
-            av.z = fmaxf(fmaf(av.z, sc.z, sh.z), 0.f); av.w = fmaxf(fmaf(av.w, sc.w, sh.w), 0.f);
+    for (int u = 0; u < U; ++u) {
+      gv[u] = make4(0.f);
+#pragma unroll
+      for (int t = 0; t < NT; ++t) av[u][t] = make4(0.f);
+      if (p + 16 * u < (unsigned)p_end) {
+        const int gy = vy * g.g_sy + tc.o_dy, gx = vx * g.g_sx + tc.o_dx;
+        if (co_ok && (unsigned)gy < (unsigned)g.GH && (unsigned)gx < (unsigned)g.GW)
+          gv[u] = ldg4(Gc + (size_t)((unsigned)(n * g.GH + gy) * (unsigned)g.GW + (unsigned)gx) * (unsigned)g.ldg);
+        const int ayb = vy * g.a_sy, axb = vx * g.a_sx;
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          const int tap = tap0 + t;
+          if (tap < tc.ntaps) {
+            const int ay = ayb + tc.a_dy[tap], ax = axb + tc.a_dx[tap];
+            if (ci_ok && (unsigned)ay < (unsigned)g.AH && (unsigned)ax < (unsigned)g.AW) {
+              av[u][t] = ldg4(Ac + (size_t)((unsigned)(n * g.AH + ay) * (unsigned)g.AW + (unsigned)ax) * (unsigned)g.lda);
+              inimg |= 1u << (u * NT + t);
+            }
           }
         }
-        const float aa[4] = {av.x, av.y, av.z, av.w};
+      }
+      vx += 16;
+      while (vx >= g.VW) { vx -= g.VW; ++vy; }
+      while (vy >= g.VH) { vy -= g.VH; ++n; }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      bsum.x += gv[u].x; bsum.y += gv[u].y; bsum.z += gv[u].z; bsum.w += gv[u].w;
+      const float gg[4] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w};
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        float4 a4 = av[u][t];
+        if (a_scale != nullptr && ((inimg >> (u * NT + t)) & 1u)) {
+          a4.x = fmaxf(fmaf(a4.x, sc.x, sh.x), 0.f); a4.y = fmaxf(fmaf(a4.y, sc.y, sh.y), 0.f);
+          a4.z = fmaxf(fmaf(a4.z, sc.z, sh.z), 0.f); a4.w = fmaxf(fmaf(a4.w, sc.w, sh.w), 0.f);
+        }
+        const float aa[4] = {a4.x, a4.y, a4.z, a4.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
           for (int j = 0; j < 4; ++j) acc[t][i][j] = fmaf(aa[i], gg[j], acc[t][i][j]);
       }
     }
-    vx += 16;
-    while (vx >= g.VW) { vx -= g.VW; ++vy; }
-    while (vy >= g.VH) { vy -= g.VH; ++n; }
   }
   // reduce over the 16 pixel lanes: lanes l and l^16 of a warp share a tile, then across the 8 warps through smem
   const int warp = tid >> 5, lane = tid & 31;
@@ -384,10 +402,10 @@ static int wgrad_small_launch(const ConvGeom& g, const float* A, const float* a_
   const int ntaps = g.cls[0].ntaps;
   const int passes = cdiv(ntaps, 3);
   size_t P = (size_t)g.N * g.VH * g.VW;
-  int want = cdiv(4 * kNumSMs, passes);
+  int want = cdiv(2 * kNumSMs, passes);    // 2 CTAs per SM, one wave
   size_t ppc = (P + want - 1) / want;
-  ppc = (ppc + 15) / 16 * 16;
-  if (ppc < 16) ppc = 16;
+  ppc = (ppc + 63) / 64 * 64;
+  if (ppc < 64) ppc = 64;
   dim3 grid((unsigned)((P + ppc - 1) / ppc), (unsigned)passes);
   wgrad_small_kernel<3><<<grid, 256, 0, s>>>(g, A, a_scale, a_shift, G, dW, s_ci, s_co, s_t, db, (int)ppc);
   MDIL_LAUNCH_CHECK();

@@ -108,6 +108,9 @@ int launch_pair_tc(const PairArgs& a, cudaStream_t s);       // nb1d_pair_tc.cu 
 int launch_pack_tc(const float* src_stream, float* dst_stream, int C, int has_adapter, cudaStream_t s);
 int launch_pair_tc3(const PairArgs& a, cudaStream_t s);      // nb1d_pair_tc3.cu (persistent pipelined tcgen05 kernel; default)
 int launch_pack_tc3(const float* src_stream, float* dst_stream, int C, int has_adapter, cudaStream_t s);
+// one launch: fp32 FFMA streams (write_fp32) and/or tensor-core images (tc_order 0 = none, 2, 3) of a whole block
+int launch_pack_block(const float* const* w6, float* packed, int C, int has_adapter, int write_fp32, int tc_order,
+                      cudaStream_t s);
 int pair_impl_mode();   // MDIL_PAIR_IMPL: 0 = "ffma", 2 = "tc2" (one tile per CTA), 3 = pipelined tensor-core kernel (default)
 void pair_profile_record_begin(const PairArgs& a, cudaStream_t s, void** rec);
 void pair_profile_record_end(cudaStream_t s, void* rec);

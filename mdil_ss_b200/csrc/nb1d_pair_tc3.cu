@@ -815,7 +815,69 @@ __global__ void pack_tc3_kernel(const float* __restrict__ src, float* __restrict
   }
 }
 
+// ---- one launch packs everything a block's four pair launches read: the fp32 [tap][cin][cout] streams of the FFMA
+// kernel (optional) and the hi/lo tensor-core images (optional; order = 2: nb1d_pair_tc.cu, 3: this kernel) straight
+// from the PyTorch-layout weights (was ~14 launches per block and step)
+struct PackSrc { const float* w[6]; };   // w31_1, w13_1, w31_2, w13_2, wp1, wp2  ([co][ci][3] / [co][ci])
+__global__ void pack_block_kernel(const PackSrc src, float* __restrict__ packed, int C, int has_adapter, int write_fp32,
+                                  int tc_order) {
+  const int CC = C * C, nch = C / KC;
+  const int per1 = 3 + (has_adapter ? 1 : 0);
+  const long total = 4L * 7 * CC;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int which = (int)(i / (7 * CC));
+    const int r = (int)(i % (7 * CC));
+    const int slab = r / CC, a = (r % CC) / C, b = r % C;
+    if (slab == 6 && !has_adapter) continue;
+    // which: 0 fwd pair 1, 1 fwd pair 2, 2 bwd pair 2, 3 bwd pair 1.  slab: 0..2 first conv taps, 3..5 second conv, 6 adapter
+    const bool bwd = which >= 2;
+    const int pairsel = (which == 0 || which == 3) ? 0 : 1;                  // weights of pair 1 or pair 2
+    float v;
+    if (slab == 6) {
+      const float* w = src.w[4 + pairsel];
+      v = bwd ? __ldg(w + a * C + b) : __ldg(w + b * C + a);                 // fwd [ci][co] = Wp[co][ci]; bwd [co][ci]
+    } else {
+      const int conv = slab / 3, tap = slab % 3;
+      // forward: first conv = 3x1, second = 1x3; backward runs the pair in reverse: first = 1x3 (flipped), second = 3x1
+      const int is13 = bwd ? (conv == 0) : (conv == 1);
+      const float* w = src.w[pairsel * 2 + is13];
+      v = bwd ? __ldg(w + ((long)a * C + b) * 3 + (2 - tap)) : __ldg(w + ((long)b * C + a) * 3 + tap);
+    }
+    if (write_fp32) packed[i] = v;
+    if (tc_order != 0) {
+      const int j = a / KC, kk = a % KC, nrow = b;
+      int g;
+      if (tc_order == 3) {
+        if (slab < 3) g = j * per1 + slab;
+        else if (slab == 6) g = j * per1 + 3;
+        else g = nch * per1 + j * 3 + (slab - 3);
+      } else {
+        if (slab < 3) g = slab * nch + j;
+        else if (slab == 6) g = 3 * nch + j;
+        else g = per1 * nch + (slab - 3) * nch + j;
+      }
+      const float hi = tf32_rna(v), lo = tf32_rna(v - hi);
+      const int off = nrow * 16 + ((((kk >> 2) ^ ((nrow >> 1) & 3)) << 2) | (kk & 3));
+      float* stage = packed + 28L * CC + (long)which * 14 * CC + (long)g * 2 * C * KC;
+      stage[off] = hi;
+      stage[C * KC + off] = lo;
+    }
+  }
+}
+
 }  // namespace tc3
+
+int launch_pack_block(const float* const* w6, float* packed, int C, int has_adapter, int write_fp32, int tc_order,
+                      cudaStream_t s) {
+  tc3::PackSrc src;
+  for (int i = 0; i < 6; ++i) src.w[i] = w6[i];
+  const long total = 4L * 7 * C * C;
+  int grid = (int)((total + 255) / 256);
+  if (grid > kNumSMs * 4) grid = kNumSMs * 4;
+  tc3::pack_block_kernel<<<grid, 256, 0, s>>>(src, packed, C, has_adapter, write_fp32, tc_order);
+  MDIL_LAUNCH_CHECK();
+  return 0;
+}
 
 int launch_pair_tc3(const PairArgs& a, cudaStream_t s) {
   switch (a.C) {

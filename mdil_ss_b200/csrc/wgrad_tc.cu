@@ -25,7 +25,13 @@ template <int C> struct Cfg {
   static constexpr uint32_t SLAB = TP * 128;                    // 32-channel slab stride (LBO)
   static constexpr uint32_t HDR = 1024;
   static constexpr uint32_t SMEM = 1024 + HDR + NST * STAGE;
-  static constexpr int TMEM_COLS = C == 128 ? 512 : 256;        // 3 accumulators of C columns, power of two
+  // C = 64: the hi and lo images are stacked along M (A) and N (G): ONE M=128, N=128 MMA per tap and K step computes
+  // [Ah;Al]^T [Gh|Gl] (all four hi/lo products) where the unstacked form needs three M=64, N=64 MMAs -- the issue rate
+  // of the single MMA thread (~100 clocks per instruction whatever the shape, tools/umma_issue*.cu) is the bound.
+  // The four 64x64 blocks of the accumulator are summed by the epilogue's red.global.add.
+  static constexpr bool STACK = C == 64;
+  static constexpr int ACCW = STACK ? 128 : C;                  // accumulator columns per tap
+  static constexpr int TMEM_COLS = 512;                         // 3 accumulators of ACCW columns, power of two
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -143,8 +149,8 @@ wgrad_tc_kernel(const __grid_constant__ WgradTcArgs a, const Plan pl) {
     // =========================================================== MMA issuer
     if (lane == 0) {
       // M = C (ci), N = C (co), both operands MN-major (bits 15, 16)
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(C >> 3) << 17) |
-                             ((uint32_t)(C >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(K::ACCW >> 3) << 17) |
+                             ((uint32_t)(K::ACCW >> 4) << 24);
       uint32_t q = 0;         // running stage-fill counter (identical on the producer side)
       uint32_t waited = 0;    // fills [0, waited) are known to have landed
       uint32_t started = 0;   // bit t set once accumulator t holds data
@@ -168,11 +174,13 @@ wgrad_tc_kernel(const __grid_constant__ WgradTcArgs a, const Plan pl) {
             for (int ks = 0; ks < TP / 8; ++ks) {
               const uint64_t ah = desc_mn(abase + ks * 1024, K::SLAB), al = desc_mn(abase + K::PART + ks * 1024, K::SLAB);
               const uint64_t gh = desc_mn(gbase + ks * 1024, K::SLAB), gl = desc_mn(gbase + K::PART + ks * 1024, K::SLAB);
-              const uint32_t acc = tmem + t * C;
-              mma_tf32(acc, ah, gh, idesc, (started >> t) & 1u);
+              const uint32_t acc = tmem + t * K::ACCW;
+              mma_tf32(acc, ah, gh, idesc, (started >> t) & 1u);     // STACK: the descriptors span hi and lo images
               started |= 1u << t;
-              mma_tf32(acc, al, gh, idesc, 1u);
-              mma_tf32(acc, ah, gl, idesc, 1u);
+              if (!K::STACK) {
+                mma_tf32(acc, al, gh, idesc, 1u);
+                mma_tf32(acc, ah, gl, idesc, 1u);
+              }
             }
           }
           // the oldest activation chunk (j-1, or j itself for the 1x1) is no longer needed once these retire
@@ -200,56 +208,93 @@ wgrad_tc_kernel(const __grid_constant__ WgradTcArgs a, const Plan pl) {
     float4 sc = make4(1.f), sh = make4(0.f);
     if (a.a_scale != nullptr) { sc = ldg4(a.a_scale + ch); sh = ldg4(a.a_shift + ch); }
     float4 bsum = make4(0.f);
+    // Fills are walked in batches of B per group: the B * 2 * RPT independent 128-bit loads of a batch are all in flight
+    // before the first one is consumed (64 KB in flight per SM instead of 16 KB: the producers were latency-bound).
+    constexpr int B = C == 128 ? 2 : 4;
+    struct FillDesc { size_t img; int u, rv, vb; uint32_t q; bool uok, interior, valid; };
+    int unit = blockIdx.x, f = 0, nfill = 0;
     uint32_t q = 0;
-    for (int unit = blockIdx.x; unit < pl.units; unit += gridDim.x) {
-      const Unit un = decode_unit(unit, pl, d);
-      const size_t img = (size_t)un.n * a.H * a.W * C;
-      const int nfill = un.Lu + 2 * pl.halo;
-      for (int f = 0; f < nfill; ++f, ++q) {
-        if ((int)(q & 1) != grp) continue;
-        const int cidx = f - pl.halo;                          // chunk index: -1 .. Lu
-        const bool interior = cidx >= 0 && cidx < un.Lu;       // carries a gradient chunk
-        const int ul = un.ul0 + cidx;
-        const int u = un.ru + d * ul;
-        const bool uok = ul >= 0 && u < pl.U;
-        float4 av[RPT], gv[RPT];
+    Unit un;
+    if (unit < pl.units) { un = decode_unit(unit, pl, d); nfill = un.Lu + 2 * pl.halo; }
+    auto next_fill = [&](FillDesc& fd) {
+      fd.valid = false;
+      while (unit < pl.units) {
+        if (f >= nfill) {
+          unit += gridDim.x;
+          f = 0;
+          if (unit < pl.units) { un = decode_unit(unit, pl, d); nfill = un.Lu + 2 * pl.halo; }
+          continue;
+        }
+        const bool mine = (int)(q & 1) == grp;
+        if (mine) {
+          const int cidx = f - pl.halo;                       // chunk index: -1 .. Lu
+          const int ul = un.ul0 + cidx;
+          fd.interior = cidx >= 0 && cidx < un.Lu;            // carries a gradient chunk
+          fd.u = un.ru + d * ul;
+          fd.uok = ul >= 0 && fd.u < pl.U;
+          fd.rv = un.rv; fd.vb = un.vb;
+          fd.img = (size_t)un.n * a.H * a.W * C;
+          fd.q = q;
+          fd.valid = true;
+        }
+        ++f; ++q;
+        if (mine) return;
+      }
+    };
+    for (;;) {
+      FillDesc fd[B];
+      float4 av[B][RPT], gv[B][RPT];
+      uint32_t inside = 0;   // bit b*RPT+i: the pixel is inside the image (BN+ReLU prologue applies)
+#pragma unroll
+      for (int b = 0; b < B; ++b) {
+        next_fill(fd[b]);
 #pragma unroll
         for (int i = 0; i < RPT; ++i) {
-          const int row = row0 + i * RSTEP;
-          const int v = un.rv + d * (un.vb * TP + row);
-          av[i] = make4(0.f);
-          gv[i] = make4(0.f);
-          if (uok && v < pl.V) {
-            const size_t off = img + u * su + v * sv + ch;
-            av[i] = ldg4(a.A + off);
-            if (a.a_scale != nullptr) {
-              av[i].x = fmaxf(fmaf(av[i].x, sc.x, sh.x), 0.f);
-              av[i].y = fmaxf(fmaf(av[i].y, sc.y, sh.y), 0.f);
-              av[i].z = fmaxf(fmaf(av[i].z, sc.z, sh.z), 0.f);
-              av[i].w = fmaxf(fmaf(av[i].w, sc.w, sh.w), 0.f);
+          av[b][i] = make4(0.f);
+          gv[b][i] = make4(0.f);
+          if (fd[b].valid) {
+            const int row = row0 + i * RSTEP;
+            const int v = fd[b].rv + d * (fd[b].vb * TP + row);
+            if (fd[b].uok && v < pl.V) {
+              const size_t off = fd[b].img + fd[b].u * su + v * sv + ch;
+              av[b][i] = ldg4(a.A + off);
+              if (fd[b].interior) gv[b][i] = ldg4(a.G + off);
+              inside |= 1u << (b * RPT + i);
             }
-            if (interior) gv[i] = ldg4(a.G + off);
           }
         }
-        if (q >= (uint32_t)NST) mbar_wait(bar_empty + 8 * (q % NST), ((q / NST) - 1) & 1);   // ring slot free?
-        const uint32_t sbase = ring + (q % NST) * K::STAGE + in_slab;
+      }
+#pragma unroll
+      for (int b = 0; b < B; ++b) {
+        if (!fd[b].valid) continue;
+        const uint32_t qq = fd[b].q;
+        if (qq >= (uint32_t)NST) mbar_wait(bar_empty + 8 * (qq % NST), ((qq / NST) - 1) & 1);   // ring slot free?
+        const uint32_t sbase = ring + (qq % NST) * K::STAGE + in_slab;
 #pragma unroll
         for (int i = 0; i < RPT; ++i) {
           const int row = row0 + i * RSTEP;
+          float4 a4 = av[b][i], g4 = gv[b][i];
+          if (a.a_scale != nullptr && ((inside >> (b * RPT + i)) & 1u)) {
+            a4.x = fmaxf(fmaf(a4.x, sc.x, sh.x), 0.f);
+            a4.y = fmaxf(fmaf(a4.y, sc.y, sh.y), 0.f);
+            a4.z = fmaxf(fmaf(a4.z, sc.z, sh.z), 0.f);
+            a4.w = fmaxf(fmaf(a4.w, sc.w, sh.w), 0.f);
+          }
           const uint32_t ra = sbase + (uint32_t)row * 128;
           const uint32_t ad = ra + (((c8 ^ ((ra >> 7) & 3)) << 5) | halfo);
           float4 hi, lo;
-          split4(av[i], hi, lo);
+          split4(a4, hi, lo);
           *reinterpret_cast<float4*>(gen + (ad - hdr)) = hi;
           *reinterpret_cast<float4*>(gen + (ad - hdr) + K::PART) = lo;
-          split4(gv[i], hi, lo);
+          split4(g4, hi, lo);
           *reinterpret_cast<float4*>(gen + (ad - hdr) + 2 * K::PART) = hi;
           *reinterpret_cast<float4*>(gen + (ad - hdr) + 3 * K::PART) = lo;
-          bsum.x += gv[i].x; bsum.y += gv[i].y; bsum.z += gv[i].z; bsum.w += gv[i].w;
+          bsum.x += g4.x; bsum.y += g4.y; bsum.z += g4.z; bsum.w += g4.w;
         }
         fence_proxy_async();
-        mbar_arrive(bar_full + 8 * (q % NST));
+        mbar_arrive(bar_full + 8 * (qq % NST));
       }
+      if (!fd[B - 1].valid) break;
     }
     if (a.db != nullptr) {
       atomicAdd(bias_red + ch + 0, bsum.x);
@@ -263,16 +308,28 @@ wgrad_tc_kernel(const __grid_constant__ WgradTcArgs a, const Plan pl) {
     __syncwarp();
     const int qd = warp & 3, half = warp >> 2;
     const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
-    // accumulator row (ci) held by this lane: M = 128 -> lane = row; M = 64 -> lanes 0..15 of each quarter hold rows 16q..16q+15
-    const int row = C == 128 ? qd * 32 + lane : qd * 16 + lane;
-    const bool row_ok = C == 128 ? true : lane < 16;
-    for (int t = 0; t < ntaps; ++t) {
+    if (K::STACK) {
+      // accumulator rows: [0,64) = A_hi channels, [64,128) = A_lo channels; columns [0,64) = G_hi, [64,128) = G_lo
+      const int ci = (qd * 32 + lane) & 63;
+      const int col0 = half * 32;
+      for (int t = 0; t < ntaps; ++t) {
+        float v1[32], v2[32];
+        tmem_ld32(tmem + lane_addr + t * K::ACCW + col0, v1);
+        tmem_ld32(tmem + lane_addr + t * K::ACCW + 64 + col0, v2);
+        float* dst = a.dWacc + ((size_t)t * C + ci) * C + col0;
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4)
+          red_add_v4(dst + j4 * 4, v1[j4 * 4 + 0] + v2[j4 * 4 + 0], v1[j4 * 4 + 1] + v2[j4 * 4 + 1], v1[j4 * 4 + 2] + v2[j4 * 4 + 2],
+                     v1[j4 * 4 + 3] + v2[j4 * 4 + 3]);
+      }
+    } else {
+      const int row = qd * 32 + lane;     // M = 128: accumulator row (ci) = TMEM lane
+      for (int t = 0; t < ntaps; ++t) {
 #pragma unroll 1
-      for (int cc = 0; cc < C / 64; ++cc) {
-        const int col0 = half * (C / 2) + cc * 32;
-        float val[32];
-        tmem_ld32(tmem + lane_addr + t * C + col0, val);
-        if (row_ok) {
+        for (int cc = 0; cc < C / 64; ++cc) {
+          const int col0 = half * (C / 2) + cc * 32;
+          float val[32];
+          tmem_ld32(tmem + lane_addr + t * K::ACCW + col0, val);
           float* dst = a.dWacc + ((size_t)t * C + row) * C + col0;
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) red_add_v4(dst + j4 * 4, val[j4 * 4 + 0], val[j4 * 4 + 1], val[j4 * 4 + 2], val[j4 * 4 + 3]);

@@ -49,6 +49,24 @@ def empty_nhwc(n: int, c: int, h: int, w: int, like: torch.Tensor) -> torch.Tens
     return torch.empty((n, h, w, c), device=like.device, dtype=torch.float32).permute(0, 3, 1, 2)
 
 
+def grad_target(param: torch.Tensor, need: bool):
+    """Where a backward kernel writes a parameter's gradient: (buffer, value returned to autograd).
+
+    Parameters whose ``.grad`` lives in a freshly zeroed flat gradient buffer (parallel.FlatAdam.zero_grad marks them
+    ``_mdil_grad_fresh``) take their FIRST gradient of the step directly in that buffer (the kernels overwrite) and
+    autograd gets None: no temporary, no accumulation kernel.  Any later contribution in the same step (a weight used
+    by two forwards, as in steps 2/3) goes through a temporary that autograd adds as usual."""
+    if not need:
+        return None, None
+    g = param.grad
+    if getattr(param, "_mdil_grad_fresh", False) and g is not None and g.is_contiguous() and g.shape == param.shape \
+            and g.device == param.device:
+        param._mdil_grad_fresh = False
+        return g, None
+    t = torch.empty_like(param)
+    return t, t
+
+
 def _bn_struct(w, b, rm, rv) -> L.BnParams:
     return L.BnParams(_ptr(w), _ptr(b), _ptr(rm), _ptr(rv))
 
@@ -137,6 +155,7 @@ class Nb1dFn(torch.autograd.Function):
         ctx.cfg = cfg
         ctx.train = bool(cfg.train)
         if need_grad:
+            ctx.param_objs = params
             ctx.save_for_backward(x, y, drop if drop is not None else torch.empty(0, device=x.device), *params)
             ctx.internal = (a, p, cc, s, stats, packed)
             ctx.has_drop = drop is not None
@@ -158,15 +177,17 @@ class Nb1dFn(torch.autograd.Function):
         with torch.cuda.device_of(x):
             wts = _nb1d_weights(params, cfg)
             grads = [None] * len(params)
+            rets = [None] * len(params)
+            objs = ctx.param_objs
             # weight/bias pairs are produced together
             pairs = [(0, 1), (2, 3), (4, 5), (6, 7)] + ([(12, 13), (14, 15)] if cfg.has_adapter else [])
             for wi, bi in pairs:
                 if needs[wi] or needs[bi]:
-                    grads[wi] = torch.empty_like(params[wi])
-                    grads[bi] = torch.empty_like(params[bi])
+                    grads[wi], rets[wi] = grad_target(objs[wi], True) if needs[wi] else (torch.empty_like(params[wi]), None)
+                    grads[bi], rets[bi] = grad_target(objs[bi], True) if needs[bi] else (torch.empty_like(params[bi]), None)
             for i in (8, 9, 10, 11):
                 if needs[i]:
-                    grads[i] = torch.empty_like(params[i])
+                    grads[i], rets[i] = grad_target(objs[i], True)
             g = L.Nb1dGrads()
             names = ["w31_1", "b31_1", "w13_1", "b13_1", "w31_2", "b31_2", "w13_2", "b13_2", "bn1_w", "bn1_b", "bn2_w",
                      "bn2_b", "wp1", "bp1", "wp2", "bp2"]
@@ -181,8 +202,7 @@ class Nb1dFn(torch.autograd.Function):
                                       ws.data_ptr(), ws_bytes, _stream()), "mdil_nb1d_bwd")
             if DEBUG_KEEP is not None:
                 DEBUG_KEEP.append(ws)
-        out_grads = [gr if need else None for gr, need in zip(grads, needs)]
-        return (dx if ctx.needs_input_grad[0] else None, None, None, *out_grads)
+        return (dx if ctx.needs_input_grad[0] else None, None, None, *rets)
 
 
 # ======================================================================================= down / up
@@ -233,6 +253,7 @@ class DownFn(torch.autograd.Function):
                     "mdil_down_fwd")
         ctx.cfg, ctx.train = cfg, bool(cfg.train)
         if need_grad:
+            ctx.param_objs = (conv_w, conv_b, bn_w, bn_b)
             ctx.save_for_backward(xk, y, conv_w, conv_b, bn_w, bn_b)
             ctx.internal = (u, stats, packed, (n, cin, h, w, cout, ldin))
         return y
@@ -249,17 +270,20 @@ class DownFn(torch.autograd.Function):
         with torch.cuda.device_of(dy):
             desc = L.DownDesc(n, h, w, cin, cout, ldin, 1, 1, BN_EPS, BN_MOMENTUM)
             dx = empty_nhwc(n, cin, h, w, dy) if need_x else None
-            dw = torch.empty_like(conv_w) if (need_w or need_b) else None
-            db = torch.empty_like(conv_b) if (need_w or need_b) else None
-            dg = torch.empty_like(bn_w) if need_g else None
-            dbe = torch.empty_like(bn_b) if need_be else None
+            pw, pb, pg, pbe = ctx.param_objs
+            dw = db = rw = rb = None
+            if need_w or need_b:
+                dw, rw = grad_target(pw, True) if need_w else (torch.empty_like(conv_w), None)
+                db, rb = grad_target(pb, True) if need_b else (torch.empty_like(conv_b), None)
+            dg, rg = grad_target(pg, need_g)
+            dbe, rbe = grad_target(pbe, need_be)
             ws_bytes = int(lib.mdil_down_workspace_bytes(C.byref(desc)))
             ws = torch.empty(ws_bytes, device=dy.device, dtype=torch.uint8)
             bn = _bn_struct(bn_w, bn_b, *ctx.cfg.bn_buffers)
             L.check(lib.mdil_down_bwd(C.byref(desc), dy.data_ptr(), xk.data_ptr(), u.data_ptr(), y.data_ptr(),
                                       stats.data_ptr(), packed.data_ptr(), C.byref(bn), _ptr(dx), _ptr(dw), _ptr(db),
                                       _ptr(dg), _ptr(dbe), ws.data_ptr(), ws_bytes, _stream()), "mdil_down_bwd")
-        return dx, None, dw if need_w else None, db if need_b else None, dg, dbe
+        return dx, None, rw, rb, rg, rbe
 
 
 class UpFn(torch.autograd.Function):
@@ -291,6 +315,7 @@ class UpFn(torch.autograd.Function):
                     "mdil_up_fwd")
         ctx.cfg, ctx.train = cfg, bool(cfg.train)
         if need_grad:
+            ctx.param_objs = (conv_w, conv_b, bn_w, bn_b)
             ctx.save_for_backward(x, y, conv_w, conv_b, bn_w, bn_b)
             ctx.internal = (u, stats, packed, (n, cin, h, w, cout))
         return y
@@ -307,17 +332,20 @@ class UpFn(torch.autograd.Function):
         with torch.cuda.device_of(dy):
             desc = L.UpDesc(n, h, w, cin, cout, 1, 1, BN_EPS, BN_MOMENTUM)
             dx = empty_nhwc(n, cin, h, w, dy) if need_x else None
-            dw = torch.empty_like(conv_w) if (need_w or need_b) else None
-            db = torch.empty_like(conv_b) if (need_w or need_b) else None
-            dg = torch.empty_like(bn_w) if need_g else None
-            dbe = torch.empty_like(bn_b) if need_be else None
+            pw, pb, pg, pbe = ctx.param_objs
+            dw = db = rw = rb = None
+            if need_w or need_b:
+                dw, rw = grad_target(pw, True) if need_w else (torch.empty_like(conv_w), None)
+                db, rb = grad_target(pb, True) if need_b else (torch.empty_like(conv_b), None)
+            dg, rg = grad_target(pg, need_g)
+            dbe, rbe = grad_target(pbe, need_be)
             ws_bytes = int(lib.mdil_up_workspace_bytes(C.byref(desc)))
             ws = torch.empty(ws_bytes, device=dy.device, dtype=torch.uint8)
             bn = _bn_struct(bn_w, bn_b, *ctx.cfg.bn_buffers)
             L.check(lib.mdil_up_bwd(C.byref(desc), dy.data_ptr(), x.data_ptr(), u.data_ptr(), y.data_ptr(),
                                     stats.data_ptr(), packed.data_ptr(), C.byref(bn), _ptr(dx), _ptr(dw), _ptr(db),
                                     _ptr(dg), _ptr(dbe), ws.data_ptr(), ws_bytes, _stream()), "mdil_up_bwd")
-        return dx, None, dw if need_w else None, db if need_b else None, dg, dbe
+        return dx, None, rw, rb, rg, rbe
 
 
 # ======================================================================================= output conv
@@ -338,6 +366,7 @@ class OutConvFn(torch.autograd.Function):
             logits = torch.empty((n, ccls, 2 * h, 2 * w), device=x.device, dtype=torch.float32)
             L.check(lib.mdil_outconv_fwd(x.data_ptr(), weight.data_ptr(), _ptr(bias), logits.data_ptr(), n, h, w, ccls,
                                          _stream()), "mdil_outconv_fwd")
+        ctx.param_objs = (weight, bias)
         ctx.save_for_backward(x, weight, bias)
         return logits
 
@@ -351,11 +380,11 @@ class OutConvFn(torch.autograd.Function):
         need_x, need_w, need_b = ctx.needs_input_grad
         with torch.cuda.device_of(x):
             dx = empty_nhwc(n, cin, h, w, x) if need_x else None
-            dw = torch.empty_like(weight) if need_w else None
-            db = torch.empty_like(bias) if need_b else None
+            dw, rw = grad_target(ctx.param_objs[0], need_w)
+            db, rb = grad_target(ctx.param_objs[1], need_b) if bias is not None else (None, None)
             L.check(lib.mdil_outconv_bwd(dlogits.data_ptr(), x.data_ptr(), weight.data_ptr(), _ptr(dx), _ptr(dw), _ptr(db),
                                          n, h, w, ccls, _stream()), "mdil_outconv_bwd")
-        return dx, dw, db
+        return dx, rw, rb
 
 
 # ======================================================================================= losses

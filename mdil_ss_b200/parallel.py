@@ -78,6 +78,9 @@ class GradAllReduce:
             for p, o, n in zip(b.params, b.offsets, b.sizes):
                 if p.grad is None or p.grad.data_ptr() != b.grad.data_ptr() + 4 * o:
                     p.grad = b.grad[o:o + n].view(p.shape)
+                # the backward kernels may write this step's first gradient straight into the buffer
+                # (functional.grad_target): saves one temporary and one accumulation kernel per parameter
+                p._mdil_grad_fresh = True
 
     def allreduce(self) -> float:
         """Returns the factor the optimiser must apply to the summed gradient (1/world)."""

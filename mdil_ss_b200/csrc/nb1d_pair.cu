@@ -166,7 +166,7 @@ __device__ __forceinline__ void mma_chunk(float (&acc)[TM][TN], const float* __r
 }
 
 template <int C>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(256, C == 16 ? 2 : 1)   // C = 16: 90 KB of shared memory per CTA, two CTAs per SM
 pair_kernel(const __grid_constant__ PairArgs a, const TileShape ts) {
   using D = PairDerived<C>;
   constexpr int TN = D::TN, TM = D::TM, NT = D::NT, MT = D::MT, CP = D::CP, NH = TN / 4;

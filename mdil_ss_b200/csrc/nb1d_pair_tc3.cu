@@ -408,6 +408,14 @@ pair_tc3_kernel(const __grid_constant__ PairArgs a, const Geo geo) {
           if (cidx < d * d && ul >= 0 && vl >= 0 && u < U && v < V) pix[p] = a.vert_first ? u * a.W + v : v * a.W + u;
         }
       }
+      // software pipeline over the slabs: the 10 loads of slab s+1 are in flight while slab s is split and stored;
+      // the loads of the first slab are issued before the operand buffer is waited for
+      float4 x[LROWS];
+#pragma unroll
+      for (int p = 0; p < LROWS; ++p) {
+        x[p] = make4(0.f);
+        if (pix[p] >= 0) x[p] = ldg4(a.in + img + (size_t)pix[p] * C + c16 * 4);
+      }
       if (it >= NBUF) {
         const long long tw0 = tracing ? clock64() : 0;
         mbar_wait(bar_buffree + 8 * b, (use - 1) & 1);
@@ -418,11 +426,11 @@ pair_tc3_kernel(const __grid_constant__ PairArgs a, const Geo geo) {
 #pragma unroll 1
       for (int slab = 0; slab < SLABS; ++slab) {
         const int ch = slab * 32 + c16 * 4;
-        float4 x[LROWS];
+        float4 xn[LROWS];
 #pragma unroll
         for (int p = 0; p < LROWS; ++p) {
-          x[p] = make4(0.f);
-          if (pix[p] >= 0) x[p] = ldg4(a.in + img + (size_t)pix[p] * C + ch);
+          xn[p] = make4(0.f);
+          if (slab + 1 < SLABS && pix[p] >= 0) xn[p] = ldg4(a.in + img + (size_t)pix[p] * C + ch + 32);
         }
         float4 sc = make4(1.f), sh = make4(0.f);
         const bool pro = a.in_scale != nullptr;
@@ -446,6 +454,8 @@ pair_tc3_kernel(const __grid_constant__ PairArgs a, const Geo geo) {
         }
         fence_proxy_async();
         mbar_arrive(bar_infull + 8 * (b * SLABS + slab));
+#pragma unroll
+        for (int p = 0; p < LROWS; ++p) x[p] = xn[p];
       }
       if (tracing && lt == 0) trc[12] += clock64() - tl0;
     }

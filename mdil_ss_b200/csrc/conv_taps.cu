@@ -8,6 +8,9 @@
 // FP32 FFMA register-tiled GEMM (8x4 / TMxTN per thread), operands staged through shared memory.
 #include "kernels.cuh"
 
+#include <stdlib.h>
+#include <string.h>
+
 namespace mdil {
 
 // ============================================================================ forward / dgrad
@@ -412,11 +415,200 @@ static int wgrad_small_launch(const ConvGeom& g, const float* A, const float* a_
   return 0;
 }
 
+// ---- skinny weight gradients on the warp-level tensor-core path (mma.sync m16n8k8, error-compensated 3xTF32, fp32
+// accumulate): M = 16 input channels, N = 8 * NTL output channels, K = pixels.  These reductions (C = 16 decoder blocks,
+// the 3->13 / 16->64 downsamplers, the 64->16 upsampler) move ~100 MB for ~1 GFLOP: they are HBM/L2-bound once the FMA
+// and shared-memory work of the generic kernels is gone.  Fragments are loaded straight from the NHWC tensors (each
+// 32-bit load instruction covers 4 pixels x 32 contiguous bytes), up to TAPS taps of one tap class per pass.
+struct MmaPass { int cls, tap0, ntaps; };
+struct MmaPlan { int npass; MmaPass pass[12]; };
+
+__device__ __forceinline__ void mma_16x8x8(float (&dd)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(dd[0]), "+f"(dd[1]), "+f"(dd[2]), "+f"(dd[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// hi = x rounded to TF32 (round-half-away on the integer pipe), lo = TF32 bits of the exact remainder
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
+  lo = __float_as_uint(x - __uint_as_float(hi)) & 0xFFFFE000u;
+}
+
+template <int NTL, int TAPS>
+__global__ void __launch_bounds__(256, 2)
+wgrad_mma_kernel(const __grid_constant__ ConvGeom g, const __grid_constant__ MmaPlan plan, const float* __restrict__ A,
+                 const float* __restrict__ a_scale, const float* __restrict__ a_shift, const float* __restrict__ G,
+                 float* __restrict__ dW, long s_ci, long s_co, long s_t, float* __restrict__ db, int pixels_per_cta) {
+  __shared__ float red[TAPS][16][8 * NTL];
+  __shared__ float bred[8 * NTL];
+  const MmaPass ps = plan.pass[blockIdx.y];
+  const TapClass& tc = g.cls[ps.cls];
+  const int ci_blocks = (g.CIN + 15) / 16;
+  const int ci0 = (blockIdx.z % ci_blocks) * 16, co0 = (blockIdx.z / ci_blocks) * (8 * NTL);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, t = lane & 3;
+  for (int i = tid; i < TAPS * 16 * 8 * NTL; i += 256) (&red[0][0][0])[i] = 0.f;
+  if (tid < 8 * NTL) bred[tid] = 0.f;
+  __syncthreads();
+  const size_t P = (size_t)g.N * g.VH * g.VW;
+  const size_t p_begin = (size_t)blockIdx.x * pixels_per_cta;
+  const size_t p_end = p_begin + pixels_per_cta < P ? p_begin + pixels_per_cta : P;
+  const int ciA = ci0 + gq, ciB = ci0 + gq + 8;
+  const bool okA = ciA < g.CIN, okB = ciB < g.CIN;
+  float scA = 1.f, shA = 0.f, scB = 1.f, shB = 0.f;
+  const bool pro = a_scale != nullptr;
+  if (pro) {
+    if (okA) { scA = __ldg(a_scale + ciA); shA = __ldg(a_shift + ciA); }
+    if (okB) { scB = __ldg(a_scale + ciB); shB = __ldg(a_shift + ciB); }
+  }
+  const bool do_bias = db != nullptr && ps.tap0 == 0 && ci0 == 0;
+  float acc[TAPS][NTL][4];
+  float bsum[NTL];
+#pragma unroll
+  for (int tp = 0; tp < TAPS; ++tp)
+#pragma unroll
+    for (int nt = 0; nt < NTL; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[tp][nt][e] = 0.f;
+#pragma unroll
+  for (int nt = 0; nt < NTL; ++nt) bsum[nt] = 0.f;
+  const float* Ab = A + g.a_coff;
+  const float* Gb = G + g.g_coff + co0 + gq;
+
+  // this lane's two pixels of the warp's 8-pixel K step: q0 = base + t, q1 = q0 + 4; the warp advances 64 pixels per step
+  unsigned q0 = (unsigned)p_begin + warp * 8 + t;
+  int vx = (int)(q0 % (unsigned)g.VW);
+  int vy = (int)((q0 / (unsigned)g.VW) % (unsigned)g.VH);
+  int n = (int)(q0 / ((unsigned)g.VW * (unsigned)g.VH));
+#pragma unroll 2
+  for (; q0 - t < (unsigned)p_end; q0 += 64) {
+    int vx1 = vx + 4, vy1 = vy, n1 = n;
+    if (vx1 >= g.VW) { vx1 -= g.VW; ++vy1; if (vy1 >= g.VH) { vy1 -= g.VH; ++n1; } }
+    const bool v0 = q0 < (unsigned)p_end, v1 = q0 + 4 < (unsigned)p_end;
+    // gradient fragments (K x N): b0 = G[q0][co], b1 = G[q1][co]
+    float gb[NTL][2];
+    {
+      const int gy0 = vy * g.g_sy + tc.o_dy, gx0 = vx * g.g_sx + tc.o_dx;
+      const int gy1 = vy1 * g.g_sy + tc.o_dy, gx1 = vx1 * g.g_sx + tc.o_dx;
+      const bool in0 = v0 && (unsigned)gy0 < (unsigned)g.GH && (unsigned)gx0 < (unsigned)g.GW;
+      const bool in1 = v1 && (unsigned)gy1 < (unsigned)g.GH && (unsigned)gx1 < (unsigned)g.GW;
+      const float* r0 = Gb + (size_t)((unsigned)(n * g.GH + gy0) * (unsigned)g.GW + (unsigned)gx0) * (unsigned)g.ldg;
+      const float* r1 = Gb + (size_t)((unsigned)(n1 * g.GH + gy1) * (unsigned)g.GW + (unsigned)gx1) * (unsigned)g.ldg;
+#pragma unroll
+      for (int nt = 0; nt < NTL; ++nt) {
+        const bool cok = co0 + nt * 8 + gq < g.COUT;
+        gb[nt][0] = (in0 && cok) ? __ldg(r0 + nt * 8) : 0.f;
+        gb[nt][1] = (in1 && cok) ? __ldg(r1 + nt * 8) : 0.f;
+      }
+    }
+    // activation fragments (M x K) per tap: a0 = A[q0+tap][ciA], a1 = A[q0+tap][ciB], a2 = A[q1+tap][ciA], a3 = A[q1+tap][ciB]
+    float af[TAPS][4];
+#pragma unroll
+    for (int tp = 0; tp < TAPS; ++tp) {
+      af[tp][0] = af[tp][1] = af[tp][2] = af[tp][3] = 0.f;
+      if (tp < ps.ntaps) {
+        const int tap = ps.tap0 + tp;
+        const int ay0 = vy * g.a_sy + tc.a_dy[tap], ax0 = vx * g.a_sx + tc.a_dx[tap];
+        const int ay1 = vy1 * g.a_sy + tc.a_dy[tap], ax1 = vx1 * g.a_sx + tc.a_dx[tap];
+        if (v0 && (unsigned)ay0 < (unsigned)g.AH && (unsigned)ax0 < (unsigned)g.AW) {
+          const float* r = Ab + (size_t)((unsigned)(n * g.AH + ay0) * (unsigned)g.AW + (unsigned)ax0) * (unsigned)g.lda;
+          if (okA) { const float x = __ldg(r + ciA); af[tp][0] = pro ? fmaxf(fmaf(x, scA, shA), 0.f) : x; }
+          if (okB) { const float x = __ldg(r + ciB); af[tp][1] = pro ? fmaxf(fmaf(x, scB, shB), 0.f) : x; }
+        }
+        if (v1 && (unsigned)ay1 < (unsigned)g.AH && (unsigned)ax1 < (unsigned)g.AW) {
+          const float* r = Ab + (size_t)((unsigned)(n1 * g.AH + ay1) * (unsigned)g.AW + (unsigned)ax1) * (unsigned)g.lda;
+          if (okA) { const float x = __ldg(r + ciA); af[tp][2] = pro ? fmaxf(fmaf(x, scA, shA), 0.f) : x; }
+          if (okB) { const float x = __ldg(r + ciB); af[tp][3] = pro ? fmaxf(fmaf(x, scB, shB), 0.f) : x; }
+        }
+      }
+    }
+    uint32_t bh[NTL][2], bl[NTL][2];
+#pragma unroll
+    for (int nt = 0; nt < NTL; ++nt) {
+      split_tf32(gb[nt][0], bh[nt][0], bl[nt][0]);
+      split_tf32(gb[nt][1], bh[nt][1], bl[nt][1]);
+      bsum[nt] += gb[nt][0] + gb[nt][1];
+    }
+#pragma unroll
+    for (int tp = 0; tp < TAPS; ++tp) {
+      uint32_t ah[4], al[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) split_tf32(af[tp][e], ah[e], al[e]);
+#pragma unroll
+      for (int nt = 0; nt < NTL; ++nt) {
+        mma_16x8x8(acc[tp][nt], ah, bh[nt]);
+        mma_16x8x8(acc[tp][nt], al, bh[nt]);
+        mma_16x8x8(acc[tp][nt], ah, bl[nt]);
+      }
+    }
+    vx += 64;
+    while (vx >= g.VW) { vx -= g.VW; ++vy; }
+    while (vy >= g.VH) { vy -= g.VH; ++n; }
+  }
+  // ---- CTA reduction in shared memory, then one atomic per output element
+#pragma unroll
+  for (int tp = 0; tp < TAPS; ++tp)
+#pragma unroll
+    for (int nt = 0; nt < NTL; ++nt) {
+      atomicAdd(&red[tp][gq][nt * 8 + 2 * t], acc[tp][nt][0]);
+      atomicAdd(&red[tp][gq][nt * 8 + 2 * t + 1], acc[tp][nt][1]);
+      atomicAdd(&red[tp][gq + 8][nt * 8 + 2 * t], acc[tp][nt][2]);
+      atomicAdd(&red[tp][gq + 8][nt * 8 + 2 * t + 1], acc[tp][nt][3]);
+    }
+  if (do_bias) {
+#pragma unroll
+    for (int nt = 0; nt < NTL; ++nt) {
+      float v = bsum[nt];
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      if (t == 0) atomicAdd(&bred[nt * 8 + gq], v);
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < TAPS * 16 * 8 * NTL; i += 256) {
+    const int tp = i / (16 * 8 * NTL), r = (i / (8 * NTL)) % 16, c = i % (8 * NTL);
+    const int ci = ci0 + r, co = co0 + c;
+    if (tp < ps.ntaps && ci < g.CIN_VALID && co < g.COUT)
+      atomicAdd(dW + (long)tc.widx[ps.tap0 + tp] * s_t + (long)ci * s_ci + (long)co * s_co, red[tp][r][c]);
+  }
+  if (do_bias && tid < 8 * NTL && co0 + tid < g.COUT) atomicAdd(db + co0 + tid, bred[tid]);
+}
+
+template <int NTL, int TAPS>
+static int wgrad_mma_launch(const ConvGeom& g, const float* A, const float* a_scale, const float* a_shift, const float* G,
+                            float* dW, long s_ci, long s_co, long s_t, float* db, cudaStream_t s) {
+  MmaPlan plan;
+  plan.npass = 0;
+  for (int c = 0; c < g.nclasses; ++c)
+    for (int t0 = 0; t0 < g.cls[c].ntaps; t0 += TAPS) {
+      MDIL_REQUIRE(plan.npass < 12, "wgrad_mma: too many tap passes");
+      plan.pass[plan.npass].cls = c;
+      plan.pass[plan.npass].tap0 = t0;
+      plan.pass[plan.npass].ntaps = g.cls[c].ntaps - t0 < TAPS ? g.cls[c].ntaps - t0 : TAPS;
+      ++plan.npass;
+    }
+  const int zb = cdiv(g.CIN, 16) * cdiv(g.COUT, 8 * NTL);
+  const size_t P = (size_t)g.N * g.VH * g.VW;
+  int want = cdiv(2 * kNumSMs, plan.npass * zb);
+  if (want < 1) want = 1;
+  size_t ppc = (P + want - 1) / want;
+  ppc = (ppc + 63) / 64 * 64;
+  if (ppc < 64) ppc = 64;
+  dim3 grid((unsigned)((P + ppc - 1) / ppc), (unsigned)plan.npass, (unsigned)zb);
+  wgrad_mma_kernel<NTL, TAPS><<<grid, 256, 0, s>>>(g, plan, A, a_scale, a_shift, G, dW, s_ci, s_co, s_t, db, (int)ppc);
+  MDIL_LAUNCH_CHECK();
+  return 0;
+}
+
 int launch_wgrad_taps(const ConvGeom& g, const float* A, const float* a_scale, const float* a_shift, const float* G,
                       float* dW, long s_ci, long s_co, long s_t, float* db, cudaStream_t s) {
   MDIL_REQUIRE(g.CIN % 4 == 0 && g.lda % 4 == 0 && g.a_coff % 4 == 0 && g.ldg % 4 == 0 && g.g_coff % 4 == 0,
                "wgrad_taps: alignment");
   MDIL_REQUIRE((size_t)g.N * g.VH * g.VW < (1ull << 31), "wgrad_taps: more than 2^31 pixels");
+  static const bool use_mma = [] { const char* e = getenv("MDIL_WGRAD_SMALL"); return !(e != nullptr && strcmp(e, "ffma") == 0); }();
+  if (use_mma && (g.CIN <= 16 || g.COUT <= 16) && g.COUT <= 48 && g.CIN <= 64) {
+    if (g.COUT <= 16) return wgrad_mma_launch<2, 3>(g, A, a_scale, a_shift, G, dW, s_ci, s_co, s_t, db, s);
+    return wgrad_mma_launch<6, 3>(g, A, a_scale, a_shift, G, dW, s_ci, s_co, s_t, db, s);
+  }
   if (g.CIN <= 16 && g.COUT <= 16 && g.nclasses == 1)
     return wgrad_small_launch(g, A, a_scale, a_shift, G, dW, s_ci, s_co, s_t, db, s);
   const int tm = g.CIN >= 128 ? 8 : (g.CIN >= 64 ? 4 : 1);

@@ -144,9 +144,14 @@ __device__ __forceinline__ float tf32_rna(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
 }
+// hi/lo split of an activation on the integer/FMA pipes (cvt.rna.tf32 runs at a fraction of their rate and was throttling
+// the math pipe of the loader and epilogue warps): hi = x rounded to TF32 (add half an ulp of the 10-bit mantissa, clear
+// the 13 low bits: round-half-away), lo = x - hi exactly (|lo| <= 2^-11 |x|).  lo is stored as is: the tensor core reads
+// only its TF32 bits (truncation, |error| < 2^-10 |lo| <= 2^-21 |x|, sign-symmetric because lo is).
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
 __device__ __forceinline__ void split4(const float4& x, float4& hi, float4& lo) {
-  hi.x = tf32_rna(x.x); hi.y = tf32_rna(x.y); hi.z = tf32_rna(x.z); hi.w = tf32_rna(x.w);
-  lo.x = tf32_rna(x.x - hi.x); lo.y = tf32_rna(x.y - hi.y); lo.z = tf32_rna(x.z - hi.z); lo.w = tf32_rna(x.w - hi.w);
+  hi.x = tf32_hi(x.x); hi.y = tf32_hi(x.y); hi.z = tf32_hi(x.z); hi.w = tf32_hi(x.w);
+  lo.x = x.x - hi.x; lo.y = x.y - hi.y; lo.z = x.z - hi.z; lo.w = x.w - hi.w;
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

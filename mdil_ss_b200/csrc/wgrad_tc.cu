@@ -369,13 +369,20 @@ int launch_c(const WgradTcArgs& a, cudaStream_t s) {
   pl.vblocks = cdiv(pl.Vl, TP);
   pl.halo = a.ntaps == 3 ? 1 : 0;
   const long strips = (long)a.N * a.dil * a.dil * pl.vblocks;
-  const int want = 2 * kNumSMs;
-  int nseg = (int)((want + strips - 1) / strips);
-  if (nseg < 1) nseg = 1;
-  int L = cdiv(pl.Ul, nseg);
-  if (L < 4) L = pl.Ul < 4 ? pl.Ul : 4;
-  pl.L = L;
-  pl.nseg = cdiv(pl.Ul, L);
+  // split every strip into nseg segments of L chunks so that the persistent grid's busiest CTA has the least work:
+  // rounds = ceil(units / SMs), each unit costs L chunks plus the 2 * halo fills of its ends
+  int best_nseg = 1;
+  double best_cost = 1e30;
+  for (int nseg = 1; nseg <= pl.Ul; ++nseg) {
+    const int L = cdiv(pl.Ul, nseg);
+    if (L < 4 && nseg > 1) break;
+    const int ns = cdiv(pl.Ul, L);
+    const long units = strips * ns;
+    const double cost = (double)cdiv((int)units, kNumSMs) * (L + 2 * pl.halo + 1);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best_nseg = ns; }
+  }
+  pl.L = cdiv(pl.Ul, best_nseg);
+  pl.nseg = cdiv(pl.Ul, pl.L);
   const long units = strips * pl.nseg;
   MDIL_REQUIRE(units > 0 && units < (1L << 30), "wgrad_tc: unit count");
   pl.units = (int)units;

@@ -120,10 +120,194 @@ conv_taps_kernel(const __grid_constant__ ConvGeom g, const float* __restrict__ A
   }
 }
 
+// ---- the same contract on the warp-level tensor-core path (mma.sync m16n8k8, 3xTF32, fp32 accumulate).
+// One warp = 16 virtual pixels x 16 output channels; K walks (tap, 16-channel group): one 128-bit load per pixel row
+// and group feeds two K steps (lane t owns channels 4t..4t+3 of the group; the weight fragment uses the same channel
+// permutation).  The CTA's [taps][CIN][16] weight slice is staged once in shared memory (row pitch 18 floats:
+// conflict-free fragment reads).  CIN = 4 (the network input, NHWC padded to 4): one K step = two taps.
+__device__ __forceinline__ void mma_16x8x8_c(float (&dd)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(dd[0]), "+f"(dd[1]), "+f"(dd[2]), "+f"(dd[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ void split_tf32_c(float x, uint32_t& hi, uint32_t& lo) {
+  hi = (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
+  lo = __float_as_uint(x - __uint_as_float(hi)) & 0xFFFFE000u;
+}
+constexpr int CM_WP = 18;   // shared-memory weight row pitch (floats)
+
+__global__ void __launch_bounds__(256, 2)
+conv_mma_kernel(const __grid_constant__ ConvGeom g, const float* __restrict__ A, const float* __restrict__ Wp,
+                const float* __restrict__ bias, float* __restrict__ out, int tiles_per_cta) {
+  extern __shared__ __align__(16) float wsm[];   // [total taps][CIN][CM_WP]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, t = lane & 3;
+  const int co0 = blockIdx.y * 16;
+  int tapbase[kMaxClasses + 1];
+  tapbase[0] = 0;
+  for (int c = 0; c < g.nclasses; ++c) tapbase[c + 1] = tapbase[c] + g.cls[c].ntaps;
+  // stage this CTA's weight slice: wsm[(slot*CIN + ci)*CM_WP + c] = Wp[widx(slot)][ci][co0 + c]
+  for (int c = 0; c < g.nclasses; ++c)
+    for (int tp = 0; tp < g.cls[c].ntaps; ++tp) {
+      const float* src = Wp + (size_t)g.cls[c].widx[tp] * g.CIN * g.COUT_PAD;
+      float* dst = wsm + (size_t)(tapbase[c] + tp) * g.CIN * CM_WP;
+      for (int i = tid; i < g.CIN * 16; i += 256) {
+        const int ci = i >> 4, cc = i & 15;
+        dst[ci * CM_WP + cc] = (co0 + cc < g.COUT_PAD) ? __ldg(src + (size_t)ci * g.COUT_PAD + co0 + cc) : 0.f;
+      }
+    }
+  __syncthreads();
+  float bv[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  if (bias != nullptr) {
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int co = co0 + nt * 8 + 2 * t + e;
+        if (co < g.COUT) bv[nt][e] = __ldg(bias + co);
+      }
+  }
+  const size_t P = (size_t)g.N * g.VH * g.VW;
+  const size_t ntiles = (P + 15) / 16;
+  const float* Ab = A + g.a_coff;
+  for (int it = 0; it < tiles_per_cta; ++it) {
+    const size_t tile = ((size_t)blockIdx.x * tiles_per_cta + it) * 8 + warp;
+    if (tile >= ntiles) break;
+    // this lane's two pixel rows of the 16-pixel tile: r0 = gq, r1 = gq + 8
+    int pn[2], py[2], px[2];
+    bool pv[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const size_t p = tile * 16 + gq + 8 * r;
+      pv[r] = p < P;
+      const unsigned p32 = pv[r] ? (unsigned)p : 0u;
+      px[r] = (int)(p32 % (unsigned)g.VW);
+      const unsigned tt = p32 / (unsigned)g.VW;
+      py[r] = (int)(tt % (unsigned)g.VH);
+      pn[r] = (int)(tt / (unsigned)g.VH);
+    }
+    for (int c = 0; c < g.nclasses; ++c) {
+      const TapClass& tc = g.cls[c];
+      float acc[2][4];
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
+      if (g.CIN == 4) {
+        for (int tp = 0; tp < tc.ntaps; tp += 2) {
+          float av[4] = {0.f, 0.f, 0.f, 0.f};   // a0: row0 tap A, a1: row1 tap A, a2: row0 tap B, a3: row1 tap B (channel t)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (tp + h >= tc.ntaps) continue;
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+              const int ay = py[r] * g.a_sy + tc.a_dy[tp + h], ax = px[r] * g.a_sx + tc.a_dx[tp + h];
+              if (pv[r] && (unsigned)ay < (unsigned)g.AH && (unsigned)ax < (unsigned)g.AW)
+                av[2 * h + r] = __ldg(Ab + (size_t)((unsigned)(pn[r] * g.AH + ay) * (unsigned)g.AW + (unsigned)ax) * (unsigned)g.lda + t);
+            }
+          }
+          uint32_t ah[4], al[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) split_tf32_c(av[e], ah[e], al[e]);
+          const float* w0 = wsm + (size_t)((tapbase[c] + tp) * 4 + t) * CM_WP;
+          const float* w1 = w0 + 4 * CM_WP;
+          const bool has1 = tp + 1 < tc.ntaps;
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt) {
+            uint32_t bh[2], bl[2];
+            split_tf32_c(w0[nt * 8 + gq], bh[0], bl[0]);
+            split_tf32_c(has1 ? w1[nt * 8 + gq] : 0.f, bh[1], bl[1]);
+            mma_16x8x8_c(acc[nt], ah, bh);
+            mma_16x8x8_c(acc[nt], al, bh);
+            mma_16x8x8_c(acc[nt], ah, bl);
+          }
+        }
+      } else {
+        for (int tp = 0; tp < tc.ntaps; ++tp) {
+          const float* ar[2];
+          bool inb[2];
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const int ay = py[r] * g.a_sy + tc.a_dy[tp], ax = px[r] * g.a_sx + tc.a_dx[tp];
+            inb[r] = pv[r] && (unsigned)ay < (unsigned)g.AH && (unsigned)ax < (unsigned)g.AW;
+            ar[r] = Ab + (size_t)((unsigned)(pn[r] * g.AH + (inb[r] ? ay : 0)) * (unsigned)g.AW + (unsigned)(inb[r] ? ax : 0)) * (unsigned)g.lda + 4 * t;
+          }
+          const float* wt = wsm + (size_t)(tapbase[c] + tp) * g.CIN * CM_WP;
+#pragma unroll 2
+          for (int cg = 0; cg < g.CIN; cg += 16) {
+            const float4 x0 = inb[0] ? ldg4(ar[0] + cg) : make4(0.f);
+            const float4 x1 = inb[1] ? ldg4(ar[1] + cg) : make4(0.f);
+            const float xa[2][4] = {{x0.x, x1.x, x0.y, x1.y}, {x0.z, x1.z, x0.w, x1.w}};   // per K step: a0..a3
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+              uint32_t ah[4], al[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) split_tf32_c(xa[ks][e], ah[e], al[e]);
+              const float* w0 = wt + (size_t)(cg + 4 * t + 2 * ks) * CM_WP;
+#pragma unroll
+              for (int nt = 0; nt < 2; ++nt) {
+                uint32_t bh[2], bl[2];
+                split_tf32_c(w0[nt * 8 + gq], bh[0], bl[0]);
+                split_tf32_c(w0[CM_WP + nt * 8 + gq], bh[1], bl[1]);
+                mma_16x8x8_c(acc[nt], ah, bh);
+                mma_16x8x8_c(acc[nt], al, bh);
+                mma_16x8x8_c(acc[nt], ah, bl);
+              }
+            }
+          }
+        }
+      }
+      // ---- epilogue of this class: rows gq / gq+8, columns co0 + nt*8 + 2t, +1
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        if (!pv[r]) continue;
+        const int oy = py[r] * g.g_sy + tc.o_dy, ox = px[r] * g.g_sx + tc.o_dx;
+        if ((unsigned)oy >= (unsigned)g.GH || (unsigned)ox >= (unsigned)g.GW) continue;
+        float* o = out + (size_t)((unsigned)(pn[r] * g.GH + oy) * (unsigned)g.GW + (unsigned)ox) * (unsigned)g.ldg + g.g_coff;
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          const int co = co0 + nt * 8 + 2 * t;
+          const float v0 = acc[nt][2 * r] + bv[nt][0], v1 = acc[nt][2 * r + 1] + bv[nt][1];
+          if (co + 1 < g.COUT && ((g.ldg | g.g_coff) & 1) == 0) *reinterpret_cast<float2*>(o + co) = make_float2(v0, v1);
+          else {
+            if (co < g.COUT) o[co] = v0;
+            if (co + 1 < g.COUT) o[co + 1] = v1;
+          }
+        }
+      }
+    }
+  }
+}
+
+static int conv_mma_launch(const ConvGeom& g, const float* A, const float* Wp, const float* bias, float* out, cudaStream_t s) {
+  int total_taps = 0;
+  for (int c = 0; c < g.nclasses; ++c) total_taps += g.cls[c].ntaps;
+  const size_t smem = (size_t)total_taps * g.CIN * CM_WP * sizeof(float);
+  MDIL_REQUIRE(smem <= 100 * 1024, "conv_mma: weight slice too large");
+  static bool attr_set = false;
+  if (!attr_set) {
+    MDIL_CUDA(cudaFuncSetAttribute(conv_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    attr_set = true;
+  }
+  const size_t P = (size_t)g.N * g.VH * g.VW;
+  const size_t ntiles = (P + 15) / 16;
+  const int coblocks = cdiv(g.COUT, 16);
+  // persistent-ish: ~4 CTAs per SM in total, each walking tiles_per_cta groups of 8 warp tiles
+  size_t groups = (ntiles + 7) / 8;
+  int want = cdiv(4 * kNumSMs, coblocks);
+  int tpc = (int)((groups + want - 1) / want);
+  if (tpc < 1) tpc = 1;
+  dim3 grid((unsigned)((groups + tpc - 1) / tpc), (unsigned)coblocks);
+  conv_mma_kernel<<<grid, 256, smem, s>>>(g, A, Wp, bias, out, tpc);
+  MDIL_LAUNCH_CHECK();
+  return 0;
+}
+
 int launch_conv_taps(const ConvGeom& g, const float* A, const float* Wp, const float* bias, float* out, cudaStream_t s) {
   MDIL_REQUIRE((size_t)g.N * g.VH * g.VW < (1ull << 31), "conv_taps: more than 2^31 pixels");
   MDIL_REQUIRE(g.CIN % 4 == 0 && g.lda % 4 == 0 && g.a_coff % 4 == 0 && g.COUT_PAD % 4 == 0, "conv_taps: alignment");
   MDIL_REQUIRE(g.nclasses >= 1 && g.nclasses <= kMaxClasses, "conv_taps: classes");
+  static const bool use_mma = [] { const char* e = getenv("MDIL_CONV_IMPL"); return !(e != nullptr && strcmp(e, "ffma") == 0); }();
+  if (use_mma && (g.CIN == 4 || g.CIN % 16 == 0)) return conv_mma_launch(g, A, Wp, bias, out, s);
   size_t P = (size_t)g.N * g.VH * g.VW;
   dim3 grid((unsigned)((P + CT_M - 1) / CT_M), (unsigned)cdiv(g.COUT, CT_N), (unsigned)g.nclasses);
   conv_taps_kernel<<<grid, 256, 0, s>>>(g, A, Wp, bias, out);

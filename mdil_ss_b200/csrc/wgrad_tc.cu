@@ -9,7 +9,7 @@
 // are then the activation chunks j-1, j, j+1 already in the shared-memory ring.  Accumulators (3 x [C x C] fp32)
 // stay in TMEM for the whole life of the persistent CTA and leave through vectorised red.global.add.v4.f32.
 //
-// Warp roles: warps 0-7 producers (two groups of 4 warps fill alternate ring stages), warp 8 lane 0 issues the MMAs.
+// Warp roles: warps 0-7 producers (two groups of 4 warps fill alternate ring stages), warps 8-10: one MMA issuer per tap.
 #include "kernels.cuh"
 
 namespace mdil {
@@ -117,7 +117,7 @@ __device__ __forceinline__ Unit decode_unit(int unit, const Plan& pl, int d) {
 }
 
 template <int C>
-__global__ void __launch_bounds__(NWORK + 32, 1)
+__global__ void __launch_bounds__(NWORK + 96, 1)
 wgrad_tc_kernel(const __grid_constant__ WgradTcArgs a, const Plan pl) {
   using K = Cfg<C>;
   constexpr int NST = K::NST;
@@ -134,8 +134,8 @@ wgrad_tc_kernel(const __grid_constant__ WgradTcArgs a, const Plan pl) {
   const long su = a.vert ? (long)a.W * C : C, sv = a.vert ? C : (long)a.W * C;
 
   if (tid == 0) {
-    for (int i = 0; i < NST; ++i) { mbar_init(bar_full + 8 * i, NWORK / 2); mbar_init(bar_empty + 8 * i, 1); }
-    mbar_init(bar_done, 1);
+    for (int i = 0; i < NST; ++i) { mbar_init(bar_full + 8 * i, NWORK / 2); mbar_init(bar_empty + 8 * i, (uint32_t)ntaps); }
+    mbar_init(bar_done, (uint32_t)ntaps);     // one commit per issuing warp
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (tid < C) bias_red[tid] = 0.f;
@@ -148,21 +148,27 @@ wgrad_tc_kernel(const __grid_constant__ WgradTcArgs a, const Plan pl) {
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - hdr));
 
-  if (warp == 8) {
-    // =========================================================== MMA issuer
-    if (lane == 0) {
-      // M = C (ci), N = C (co), both operands MN-major (bits 15, 16)
+  if (warp >= 8) {
+    // =========================================================== MMA issuers: one warp (one lane) per tap.  A thread
+    // issues a tcgen05.mma only every ~100 clocks whatever its shape (tools/umma_issue*.cu), so the three taps, which
+    // own separate TMEM accumulators, are issued by three warps in parallel; each accumulator still receives an
+    // ordered sequence of MMAs from a single thread (deterministic).
+    const int t = warp - 8;
+    if (lane == 0 && t < ntaps) {
+      // M = N = ACCW, both operands MN-major (bits 15, 16)
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(K::ACCW >> 3) << 17) |
                              ((uint32_t)(K::ACCW >> 4) << 24);
+      const uint32_t acc = tmem + t * K::ACCW;
       uint32_t q = 0;         // running stage-fill counter (identical on the producer side)
       uint32_t waited = 0;    // fills [0, waited) are known to have landed
-      uint32_t started = 0;   // bit t set once accumulator t holds data
+      uint32_t started = 0;
       for (int unit = blockIdx.x; unit < pl.units; unit += gridDim.x) {
         const Unit un = decode_unit(unit, pl, d);
         const uint32_t q0 = q;
-        // chunk c (c = -halo .. Lu-1+halo) is fill q0 + c + halo
+        // chunk c (c = -halo .. Lu-1+halo) is fill q0 + c + halo.  Tap t of gradient chunk j reads the gradient of fill
+        // q0+j+halo and the activation of fill q0+j+t: the newest fill it needs is q0 + j + max(halo, t)
         for (int j = 0; j < un.Lu; ++j) {
-          const uint32_t need = q0 + j + 2 * pl.halo + 1;   // fills up to chunk j+halo
+          const uint32_t need = q0 + j + (uint32_t)(pl.halo > t ? pl.halo : t) + 1;
           while (waited < need) {
             mbar_wait(bar_full + 8 * (waited % NST), (waited / NST) & 1);
             ++waited;
@@ -170,23 +176,21 @@ wgrad_tc_kernel(const __grid_constant__ WgradTcArgs a, const Plan pl) {
           tc_fence_after();
           const uint32_t fg = q0 + j + pl.halo;             // fill holding gradient chunk j (and activation chunk j)
           const uint32_t gbase = ring + (fg % NST) * K::STAGE + 2 * K::PART;
-          for (int t = 0; t < ntaps; ++t) {
-            const uint32_t fa = fg + t - pl.halo;           // activation chunk j + t - 1 (or j for the 1x1)
-            const uint32_t abase = ring + (fa % NST) * K::STAGE;
+          const uint32_t fa = fg + t - pl.halo;             // activation chunk j + t - 1 (or j for the 1x1)
+          const uint32_t abase = ring + (fa % NST) * K::STAGE;
 #pragma unroll
-            for (int ks = 0; ks < TP / 8; ++ks) {
-              const uint64_t ah = desc_mn(abase + ks * 1024, K::SLAB), al = desc_mn(abase + K::PART + ks * 1024, K::SLAB);
-              const uint64_t gh = desc_mn(gbase + ks * 1024, K::SLAB), gl = desc_mn(gbase + K::PART + ks * 1024, K::SLAB);
-              const uint32_t acc = tmem + t * K::ACCW;
-              mma_tf32(acc, ah, gh, idesc, (started >> t) & 1u);     // STACK: the descriptors span hi and lo images
-              started |= 1u << t;
-              if (!K::STACK) {
-                mma_tf32(acc, al, gh, idesc, 1u);
-                mma_tf32(acc, ah, gl, idesc, 1u);
-              }
+          for (int ks = 0; ks < TP / 8; ++ks) {
+            const uint64_t ah = desc_mn(abase + ks * 1024, K::SLAB), al = desc_mn(abase + K::PART + ks * 1024, K::SLAB);
+            const uint64_t gh = desc_mn(gbase + ks * 1024, K::SLAB), gl = desc_mn(gbase + K::PART + ks * 1024, K::SLAB);
+            mma_tf32(acc, ah, gh, idesc, started);     // STACK: the descriptors span hi and lo images
+            started = 1u;
+            if (!K::STACK) {
+              mma_tf32(acc, al, gh, idesc, 1u);
+              mma_tf32(acc, ah, gl, idesc, 1u);
             }
           }
-          // the oldest activation chunk (j-1, or j itself for the 1x1) is no longer needed once these retire
+          // fill q0+j (activation chunk j-1 / the 1x1's chunk j) is not read by this tap after these retire:
+          // tap 0 read it as its activation now, tap 1 at chunk j-1 (and its gradient then), tap 2 at chunk j-2
           umma_commit(bar_empty + 8 * ((q0 + j) % NST));
         }
         if (pl.halo) {   // the last two fills of the unit (chunks Lu-1 and Lu)
@@ -391,7 +395,7 @@ int launch_c(const WgradTcArgs& a, cudaStream_t s) {
   pl.units = (int)units;
   const int grid = (int)(units < kNumSMs ? units : kNumSMs);
   MDIL_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM));
-  wgrad_tc_kernel<C><<<grid, NWORK + 32, K::SMEM, s>>>(a, pl);
+  wgrad_tc_kernel<C><<<grid, NWORK + 96, K::SMEM, s>>>(a, pl);
   MDIL_LAUNCH_CHECK();
   return 0;
 }

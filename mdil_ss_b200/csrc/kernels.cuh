@@ -126,6 +126,7 @@ struct WgradTcArgs {
   float* dWacc;            // [ntaps][C(ci)][C(co)] fp32, zeroed by the caller (accumulated with red.global.add)
   float* db;               // nullable [C], zeroed by the caller
   int N, H, W, C, dil, ntaps, vert;
+  int trace;               // debug: CTA 0 prints its wait counters (MDIL_TC_TRACE=1)
 };
 int launch_wgrad_tc(const WgradTcArgs& a, cudaStream_t s);
 int launch_wgrad_unpack(const float* acc, float* dW, int C, int ntaps, long s_ci, long s_co, long s_t, cudaStream_t s);

@@ -12,6 +12,9 @@
 // Warp roles: warps 0-7 producers (two groups of 4 warps fill alternate ring stages), warps 8-10: one MMA issuer per tap.
 #include "kernels.cuh"
 
+#include <stdio.h>
+#include <stdlib.h>
+
 namespace mdil {
 namespace wtc {
 
@@ -127,7 +130,9 @@ wgrad_tc_kernel(const __grid_constant__ WgradTcArgs a, const Plan pl) {
   unsigned char* gen = smem_raw + (hdr - raw);
   const uint32_t bar_full = hdr, bar_empty = hdr + 8 * NST, bar_done = hdr + 16 * NST, tmem_slot = bar_done + 16;
   const uint32_t ring = hdr + K::HDR;
-  float* bias_red = reinterpret_cast<float*>(gen + 512);   // [C] (C <= 128)
+  float* bias_red = reinterpret_cast<float*>(gen + 256);   // [C] (C <= 128): bytes [256, 768)
+  long long* trc = reinterpret_cast<long long*>(gen + 768);  // trace counters of CTA 0 (a.trace)
+  const bool tracing = a.trace != 0 && blockIdx.x == 0;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int d = a.dil, ntaps = a.ntaps;
@@ -139,6 +144,8 @@ wgrad_tc_kernel(const __grid_constant__ WgradTcArgs a, const Plan pl) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (tid < C) bias_red[tid] = 0.f;
+  if (tracing && tid < 16) trc[tid] = 0;
+  const long long t_start = tracing ? clock64() : 0;
   if (warp == 8) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(K::TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -169,10 +176,12 @@ wgrad_tc_kernel(const __grid_constant__ WgradTcArgs a, const Plan pl) {
         // q0+j+halo and the activation of fill q0+j+t: the newest fill it needs is q0 + j + max(halo, t)
         for (int j = 0; j < un.Lu; ++j) {
           const uint32_t need = q0 + j + (uint32_t)(pl.halo > t ? pl.halo : t) + 1;
+          const long long tw0 = tracing ? clock64() : 0;
           while (waited < need) {
             mbar_wait(bar_full + 8 * (waited % NST), (waited / NST) & 1);
             ++waited;
           }
+          if (tracing) trc[t] += clock64() - tw0;
           tc_fence_after();
           const uint32_t fg = q0 + j + pl.halo;             // fill holding gradient chunk j (and activation chunk j)
           const uint32_t gbase = ring + (fg % NST) * K::STAGE + 2 * K::PART;
@@ -217,7 +226,7 @@ wgrad_tc_kernel(const __grid_constant__ WgradTcArgs a, const Plan pl) {
     float4 bsum = make4(0.f);
     // Fills are walked in batches of B per group: the B * 2 * RPT independent 128-bit loads of a batch are all in flight
     // before the first one is consumed (64 KB in flight per SM instead of 16 KB: the producers were latency-bound).
-    constexpr int B = C == 128 ? 2 : 4;
+    constexpr int B = C == 128 ? 1 : 2;
     struct FillDesc { size_t img; int u, rv, vb; uint32_t q; bool uok, interior, valid; };
     int unit = blockIdx.x, f = 0, nfill = 0;
     uint32_t q = 0;
@@ -248,10 +257,9 @@ wgrad_tc_kernel(const __grid_constant__ WgradTcArgs a, const Plan pl) {
         if (mine) return;
       }
     };
-    for (;;) {
-      FillDesc fd[B];
-      float4 av[B][RPT], gv[B][RPT];
-      uint32_t inside = 0;   // bit b*RPT+i: the pixel is inside the image (BN+ReLU prologue applies)
+    // register double buffer: the loads of batch n+1 are issued before batch n is split and stored
+    auto load_batch = [&](FillDesc (&fd)[B], float4 (&av)[B][RPT], float4 (&gv)[B][RPT], uint32_t& inside) {
+      inside = 0;   // bit b*RPT+i: the pixel is inside the image (BN+ReLU prologue applies)
 #pragma unroll
       for (int b = 0; b < B; ++b) {
         next_fill(fd[b]);
@@ -271,11 +279,15 @@ wgrad_tc_kernel(const __grid_constant__ WgradTcArgs a, const Plan pl) {
           }
         }
       }
+    };
+    auto store_batch = [&](const FillDesc (&fd)[B], const float4 (&av)[B][RPT], const float4 (&gv)[B][RPT], uint32_t inside) {
 #pragma unroll
       for (int b = 0; b < B; ++b) {
         if (!fd[b].valid) continue;
         const uint32_t qq = fd[b].q;
+        const long long tw0 = tracing ? clock64() : 0;
         if (qq >= (uint32_t)NST) mbar_wait(bar_empty + 8 * (qq % NST), ((qq / NST) - 1) & 1);   // ring slot free?
+        if (tracing && tg == 0) trc[4 + grp] += clock64() - tw0;
         const uint32_t sbase = ring + (qq % NST) * K::STAGE + in_slab;
 #pragma unroll
         for (int i = 0; i < RPT; ++i) {
@@ -301,7 +313,20 @@ wgrad_tc_kernel(const __grid_constant__ WgradTcArgs a, const Plan pl) {
         fence_proxy_async();
         mbar_arrive(bar_full + 8 * (qq % NST));
       }
-      if (!fd[B - 1].valid) break;
+    };
+    {
+      FillDesc fd0[B], fd1[B];
+      float4 av0[B][RPT], gv0[B][RPT], av1[B][RPT], gv1[B][RPT];
+      uint32_t in0, in1;
+      load_batch(fd0, av0, gv0, in0);
+      for (;;) {
+        if (!fd0[0].valid) break;
+        load_batch(fd1, av1, gv1, in1);
+        store_batch(fd0, av0, gv0, in0);
+        if (!fd1[0].valid) break;
+        load_batch(fd0, av0, gv0, in0);
+        store_batch(fd1, av1, gv1, in1);
+      }
     }
     if (a.db != nullptr) {
       atomicAdd(bias_red + ch + 0, bsum.x);
@@ -310,42 +335,65 @@ wgrad_tc_kernel(const __grid_constant__ WgradTcArgs a, const Plan pl) {
       atomicAdd(bias_red + ch + 3, bsum.w);
     }
     // =========================================================== epilogue: TMEM -> red.global.add.v4
+    if (tracing && tid == 0) trc[6] = clock64() - t_start;
     mbar_wait(bar_done, 0);
+    if (tracing && tid == 0) trc[7] = clock64() - t_start;
     tc_fence_after();
     __syncwarp();
     const int qd = warp & 3, half = warp >> 2;
     const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
+    // Every CTA adds its partial [ntaps][C][C] into the same buffer: the walk over taps and 16-byte pieces is rotated by
+    // the CTA index so that concurrent CTAs hit different addresses (same-address L2 atomics serialise).
+    const int rot = (int)blockIdx.x;
     if (K::STACK) {
       // accumulator rows: [0,64) = A_hi channels, [64,128) = A_lo channels; columns [0,64) = G_hi, [64,128) = G_lo
       const int ci = (qd * 32 + lane) & 63;
       const int col0 = half * 32;
-      for (int t = 0; t < ntaps; ++t) {
+      for (int tt = 0; tt < ntaps; ++tt) {
+        const int t = (tt + rot) % ntaps;
         float v1[32], v2[32];
         tmem_ld32(tmem + lane_addr + t * K::ACCW + col0, v1);
         tmem_ld32(tmem + lane_addr + t * K::ACCW + 64 + col0, v2);
         float* dst = a.dWacc + ((size_t)t * C + ci) * C + col0;
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4)
-          red_add_v4(dst + j4 * 4, v1[j4 * 4 + 0] + v2[j4 * 4 + 0], v1[j4 * 4 + 1] + v2[j4 * 4 + 1], v1[j4 * 4 + 2] + v2[j4 * 4 + 2],
-                     v1[j4 * 4 + 3] + v2[j4 * 4 + 3]);
+        for (int jj = 0; jj < 8; ++jj) {
+          const int j4 = (jj + (rot >> 2)) & 7;   // (static register indexing is kept by the select chain below)
+          float x0 = 0.f, x1 = 0.f, x2 = 0.f, x3 = 0.f;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (k == j4) { x0 = v1[k * 4 + 0] + v2[k * 4 + 0]; x1 = v1[k * 4 + 1] + v2[k * 4 + 1]; x2 = v1[k * 4 + 2] + v2[k * 4 + 2]; x3 = v1[k * 4 + 3] + v2[k * 4 + 3]; }
+          red_add_v4(dst + j4 * 4, x0, x1, x2, x3);
+        }
       }
     } else {
       const int row = qd * 32 + lane;     // M = 128: accumulator row (ci) = TMEM lane
-      for (int t = 0; t < ntaps; ++t) {
+      for (int tt = 0; tt < ntaps; ++tt) {
+        const int t = (tt + rot) % ntaps;
 #pragma unroll 1
-        for (int cc = 0; cc < C / 64; ++cc) {
+        for (int c2 = 0; c2 < C / 64; ++c2) {
+          const int cc = (c2 + (rot >> 5)) % (C / 64);
           const int col0 = half * (C / 2) + cc * 32;
           float val[32];
           tmem_ld32(tmem + lane_addr + t * K::ACCW + col0, val);
           float* dst = a.dWacc + ((size_t)t * C + row) * C + col0;
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) red_add_v4(dst + j4 * 4, val[j4 * 4 + 0], val[j4 * 4 + 1], val[j4 * 4 + 2], val[j4 * 4 + 3]);
+          for (int jj = 0; jj < 8; ++jj) {
+            const int j4 = (jj + (rot >> 2)) & 7;
+            float x0 = 0.f, x1 = 0.f, x2 = 0.f, x3 = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              if (k == j4) { x0 = val[k * 4 + 0]; x1 = val[k * 4 + 1]; x2 = val[k * 4 + 2]; x3 = val[k * 4 + 3]; }
+            red_add_v4(dst + j4 * 4, x0, x1, x2, x3);
+          }
         }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (tracing && tid == 0)
+    printf("wgrad_tc<%d> CTA0 taps=%d units=%d: total %lld clk | issuers waited for fills %lld %lld %lld | producers waited for slots %lld %lld | producers done %lld, MMAs done %lld\n",
+           C, ntaps, pl.units, clock64() - t_start, trc[0], trc[1], trc[2], trc[4], trc[5], trc[6], trc[7]);
   if (a.db != nullptr && tid < C) atomicAdd(a.db + tid, bias_red[tid]);
   if (warp == 8) {
     __syncwarp();
@@ -402,7 +450,10 @@ int launch_c(const WgradTcArgs& a, cudaStream_t s) {
 
 }  // namespace wtc
 
-int launch_wgrad_tc(const WgradTcArgs& a, cudaStream_t s) {
+int launch_wgrad_tc(const WgradTcArgs& a_in, cudaStream_t s) {
+  static const int trace = getenv("MDIL_TC_TRACE") != nullptr ? 1 : 0;
+  WgradTcArgs a = a_in;
+  a.trace = trace;
   MDIL_REQUIRE(a.ntaps == 1 || a.ntaps == 3, "wgrad_tc: 1 or 3 taps");
   MDIL_REQUIRE(a.dWacc != nullptr && ((uintptr_t)a.dWacc & 15) == 0, "wgrad_tc: accumulator buffer");
   switch (a.C) {

@@ -282,13 +282,23 @@ def run_ours(args):
         c = (16, 64, 128)[kind // 4]
         hh, ww = {16: (H // 2, W // 2), 64: (H // 4, W // 4), 128: (H // 8, W // 8)}[c]
         T = 4.0 * n * c * hh * ww
-        alg_bytes = 2.0 * T  # read the pair's input tensor once, write its output tensor once
+        # ALGORITHMIC bytes of one launch (SURVEY 8d / DESIGN.md 4), T = one tensor pass: forward pairs read their input
+        # and write their output (2T); backward pair 2 = the "main pass" (R ds, c-mask, p; W dq: 4T); backward pair 1 =
+        # the "input pass" (R dp, a-mask, dy, y; W dx: 5T).  The saved / gradient `mid` tensor a launch also writes is
+        # not counted (it is an implementation choice: 180 GB of HBM make recomputation unnecessary).
+        passes = (2.0, 2.0, 4.0, 5.0)[kind % 4]
+        alg_bytes = passes * T
         avg_ms = tot[kind] / max(1, cnt[kind])
         achieved = alg_bytes / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
         pair_share = sum(tot) / ms_total if ms_total > 0 else 0.0
+        traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kind, from the committed ncu capture
+        try:
+            traffic = json.load(open(os.path.join(REPO, "profiles", "pair_traffic.json"))).get(names[kind])
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                    "traffic": None, "kernel": names[kind], "avg_launch_ms": avg_ms, "launches_timed": int(cnt[kind]),
-                    "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                    "traffic": traffic, "kernel": names[kind], "avg_launch_ms": avg_ms, "launches_timed": int(cnt[kind]),
+                    "algorithmic_bytes_per_launch": alg_bytes, "algorithmic_tensor_passes": passes, "peak_source": peak_src,
                     "pair_kernels_share_of_step": pair_share,
                     "per_kind_ms_per_step": {names[i]: tot[i] / args.steps for i in range(nk) if cnt[i]}}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

@@ -36,16 +36,16 @@ constexpr int LROWS = IN_MAX / 16;   // rows per loader thread and slab
 
 template <int C> struct Cfg {
   static constexpr int NBUF = C == 64 ? 2 : 1;              // activation operand buffers
-  static constexpr int NSTAGE = C == 64 ? 6 : 3;            // weight ring depth
+  static constexpr int NSTAGE = C == 64 ? 8 : 4;            // weight ring depth
   static constexpr int SLABS = C / 32;
   static constexpr uint32_t SLAB_BYTES = IN_MAX * 128;
   static constexpr uint32_t ACT_BYTES = SLABS * SLAB_BYTES;  // one (hi or lo) operand image
   static constexpr uint32_t BUF_BYTES = 2 * ACT_BYTES;
   static constexpr uint32_t HALF_STAGE = C * 64;             // one (hi or lo) weight image of a chunk
   static constexpr uint32_t STAGE_BYTES = 2 * HALF_STAGE;
-  static constexpr uint32_t HDR_BYTES = 1024;                // barriers | tmem slot | trace
-  static constexpr uint32_t STG_BYTES = 8 * 2048;            // one [32 rows][16 ch] fp32 staging tile per epilogue warp
-  static constexpr uint32_t SMEM_BYTES = 1024 + HDR_BYTES + NBUF * BUF_BYTES + NSTAGE * STAGE_BYTES + STG_BYTES;
+  static constexpr uint32_t HDR_BYTES = 2048;                // barriers | tmem slot | trace | [2][C] BatchNorm sums
+  static constexpr uint32_t SUM_OFF = 1024;
+  static constexpr uint32_t SMEM_BYTES = 1024 + HDR_BYTES + NBUF * BUF_BYTES + NSTAGE * STAGE_BYTES;
   static constexpr int NCH = C / KC;
   static constexpr int NSB = C / 32;                         // 16-column sub-blocks per epilogue warp
   // C = 64: the hi and lo weight images of a chunk are stacked along N (one MMA with N = 2C computes x*Whi into columns
@@ -120,6 +120,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+// 16 TMEM lanes x 16 columns: lane l gets rows (l>>2), (l>>2)+8 and columns 2(l&3), +1 of each 8-column group:
+// v[4c + 2k + e] = (row (l>>2) + 8k, column 8c + 2(l&3) + e).  No wait: several loads may be in flight.
+__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // sum of two 16-column accumulator pieces (both loads in flight, one wait)
 __device__ __forceinline__ void tmem_ld16x2(uint32_t ta, uint32_t tb, float (&v)[16]) {
   uint32_t r[16], q[16];
@@ -229,7 +240,6 @@ pair_tc3_kernel(const __grid_constant__ PairArgs a, const Geo geo) {
   long long* trc = reinterpret_cast<long long*>(gen + 256);   // trace counters of CTA 0 (a.trace)
   const uint32_t act0 = hdr + K::HDR_BYTES;
   const uint32_t ring = act0 + NBUF * K::BUF_BYTES;
-  const uint32_t stg_off = K::HDR_BYTES + NBUF * K::BUF_BYTES + NSTAGE * K::STAGE_BYTES;
   const bool tracing = a.trace != 0 && blockIdx.x == 0;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -466,46 +476,90 @@ pair_tc3_kernel(const __grid_constant__ PairArgs a, const Geo geo) {
     }
   } else {
     // ============================================================ epilogue warps
+    // TMEM is read with the 16x256b shape: lane l holds rows (l>>2) and (l>>2)+8 of a 16-lane half and columns
+    // 2(l&3), 2(l&3)+1 of every 8-column group, i.e. four lanes own 32 contiguous bytes of an NHWC pixel row: epilogue
+    // inputs are loaded and results stored with 8-byte accesses that fill whole 32-byte sectors, without staging
+    // through shared memory (tools/tmem_probe.cu prints the fragment layout).
     const int q = warp & 3, half = warp >> 2;
-    const int m = q * 32 + lane;                               // accumulator row (TMEM lane) of this thread
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    const int mu = m / RT, rem_m = m % RT;
-    const int rcls = rem_m / TVH, mv = rem_m % TVH;
-    float* stg = reinterpret_cast<float*>(gen + stg_off + (size_t)warp * 2048);
-    const int rsub8 = lane >> 2, c4 = lane & 3;                // coalesced view: 8 rows x 4 float4 per instruction
-    const int sumch = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-    float s1acc[K::NSB], s2acc[K::NSB];
+    const int lr = lane >> 2, lc = (lane & 3) * 2;             // row within a group of 8, first of this lane's 2 columns
+    // this lane's four accumulator rows: m(h,k) = 32q + 16h + 8k + lr; their tile-independent decomposition
+    int rdec[4];
 #pragma unroll
-    for (int i = 0; i < K::NSB; ++i) { s1acc[i] = 0.f; s2acc[i] = 0.f; }
+    for (int r = 0; r < 4; ++r) {
+      const int m = q * 32 + (r >> 1) * 16 + (r & 1) * 8 + lr;
+      const int mu = m / RT, rem_m = m % RT;
+      rdec[r] = (m < M1) ? (mu | ((rem_m / TVH) << 8) | ((rem_m % TVH) << 16)) : -1;
+    }
+    float* ssum = reinterpret_cast<float*>(gen + K::SUM_OFF);   // [2][C] per-CTA BatchNorm sums
+    if (a.sums != nullptr) {
+      for (int i = tid; i < 2 * C; i += N_EPI) ssum[i] = 0.f;
+      named_bar_sync(1, N_EPI);
+    }
 
     for (int it = 0; it < ntiles; ++it) {
       const int b = it % NBUF, a2 = it & 1;
       const TileCoord tcd = decode(it);
       const size_t img = (size_t)tcd.n * a.H * a.W * C;
-      const int cidx = tcd.cb * TR + rcls;
-      const bool cls_ok = !tcd.dummy && m < M1 && cidx < d * d;
-      const int ru = cidx / d, rv = cidx % d;
-      const int u = ru + d * (tcd.ul0 + mu);
-      const int vm = rv + d * (tcd.vl0 - 1 + mv), vo = rv + d * (tcd.vl0 + mv);
-      const bool mid_valid = cls_ok && (tcd.vl0 - 1 + mv) >= 0 && u < U && vm < V;
-      const bool out_valid = cls_ok && mv < TV && u < U && vo < V;
-      const int pix_mid = mid_valid ? (a.vert_first ? u * a.W + vm : vm * a.W + u) : -1;
-      const int pix_out = out_valid ? (a.vert_first ? u * a.W + vo : vo * a.W + u) : -1;
+      int pix_mid[4], pix_out[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        pix_mid[r] = -1; pix_out[r] = -1;
+        if (rdec[r] >= 0 && !tcd.dummy) {
+          const int mu = rdec[r] & 0xFF, rcls = (rdec[r] >> 8) & 0xFF, mv = rdec[r] >> 16;
+          const int cidx = tcd.cb * TR + rcls;
+          if (cidx < d * d) {
+            const int ru = cidx / d, rv = cidx % d;
+            const int u = ru + d * (tcd.ul0 + mu);
+            const int vm = rv + d * (tcd.vl0 - 1 + mv), vo = rv + d * (tcd.vl0 + mv);
+            if ((tcd.vl0 - 1 + mv) >= 0 && u < U && vm < V) pix_mid[r] = a.vert_first ? u * a.W + vm : vm * a.W + u;
+            if (mv < TV && u < U && vo < V) pix_out[r] = a.vert_first ? u * a.W + vo : vo * a.W + u;
+          }
+        }
+      }
       unsigned char* hi_base = gen + K::HDR_BYTES + (size_t)b * K::BUF_BYTES;
       const uint32_t acc2 = tmem + K::ACCW + (uint32_t)a2 * K::ACCW;
+      // accumulator sub-block i of this warp (columns ch0 .. ch0+15) -> v[r][c][e]: row r (0..3), 8-column group c, column e
+      auto load_acc = [&](uint32_t acc, int ch0, float (&v)[4][2][2]) {
+        float t0[8], t1[8];
+        if (K::NSTACK) {
+          float u0[8], u1[8];
+          tmem_ld_16x256b_x2(acc + lane_addr + ch0, t0);
+          tmem_ld_16x256b_x2(acc + lane_addr + (16u << 16) + ch0, t1);
+          tmem_ld_16x256b_x2(acc + lane_addr + C + ch0, u0);
+          tmem_ld_16x256b_x2(acc + lane_addr + (16u << 16) + C + ch0, u1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { t0[j] += u0[j]; t1[j] += u1[j]; }
+        } else {
+          tmem_ld_16x256b_x2(acc + lane_addr + ch0, t0);
+          tmem_ld_16x256b_x2(acc + lane_addr + (16u << 16) + ch0, t1);
+          tmem_ld_wait();
+        }
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int k = 0; k < 2; ++k)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              v[k][c][e] = t0[4 * c + 2 * k + e];        // half 0: rows lr, lr+8
+              v[2 + k][c][e] = t1[4 * c + 2 * k + e];    // half 1: rows 16+lr, 24+lr
+            }
+      };
+      // 8-byte loads of this lane's elements of a [pixel][C] tensor for sub-block i (zero where the row has no pixel)
+      auto fetch2 = [&](const float* base, const int (&pix)[4], int ch0, float2 (&dst)[4][2]) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            dst[r][c] = make_float2(0.f, 0.f);
+            if (pix[r] >= 0) dst[r][c] = __ldg(reinterpret_cast<const float2*>(base + img + (size_t)pix[r] * C + ch0 + 8 * c + lc));
+          }
+      };
 
       // ================================================== epilogue 1: mid = f(acc1) -> hi/lo A operand (rows m)
-      float4 pre[4], pre2[4];
-      auto fetch_mask = [&](int i) {     // coalesced ReLU-mask tile of sub-block i -> registers
-        const int ch0 = (2 * i + half) * 16;
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          const int pix = __shfl_sync(0xffffffffu, pix_mid, 8 * kk + rsub8);
-          pre[kk] = make4(0.f);
-          if (pix >= 0) pre[kk] = ldg4(a.mid_mask + img + (size_t)pix * C + ch0 + c4 * 4);
-        }
-      };
-      if (a.mid_mask != nullptr) fetch_mask(0);
+      float2 pre[4][2], pre2[4][2];
+      if (a.mid_mask != nullptr) fetch2(a.mid_mask, pix_mid, half * 16, pre);
       {
         const long long tw0 = tracing ? clock64() : 0;
         mbar_wait(bar_acc1full, it & 1);
@@ -516,89 +570,55 @@ pair_tc3_kernel(const __grid_constant__ PairArgs a, const Geo geo) {
 #pragma unroll 1
       for (int i = 0; i < K::NSB; ++i) {
         const int ch0 = (2 * i + half) * 16;
-        float val[16];
-        float mk[16];
+        float v[4][2][2];
+        float2 mk[4][2];
         if (a.mid_mask != nullptr) {
-          __syncwarp();
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) *stg_ptr(stg, 8 * kk + rsub8, c4) = pre[kk];
-          __syncwarp();
+          for (int r = 0; r < 4; ++r)
 #pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            const float4 t4 = *stg_ptr(stg, lane, j4);
-            mk[j4 * 4 + 0] = t4.x; mk[j4 * 4 + 1] = t4.y; mk[j4 * 4 + 2] = t4.z; mk[j4 * 4 + 3] = t4.w;
-          }
-          if (i + 1 < K::NSB) fetch_mask(i + 1);
+            for (int c = 0; c < 2; ++c) mk[r][c] = pre[r][c];
+          if (i + 1 < K::NSB) fetch2(a.mid_mask, pix_mid, ch0 + 32, pre);
         }
-        if (K::NSTACK) tmem_ld16x2(acc1 + lane_addr + ch0, acc1 + lane_addr + C + ch0, val);
-        else tmem_ld16(acc1 + lane_addr + ch0, val);
-        if (mid_valid) {
-          if (a.mid_mask != nullptr) {
+        load_acc(acc1, ch0, v);
+        float2 bb[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+        if (a.mid_mask == nullptr && a.b1 != nullptr) {
+          bb[0] = __ldg(reinterpret_cast<const float2*>(a.b1 + ch0 + lc));
+          bb[1] = __ldg(reinterpret_cast<const float2*>(a.b1 + ch0 + 8 + lc));
+        }
+        unsigned char* slab_hi = hi_base + (size_t)(ch0 >> 5) * K::SLAB_BYTES;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) val[j] = mk[j] > 0.f ? val[j] : 0.f;
-          } else {
+        for (int r = 0; r < 4; ++r) {
+          const int m = q * 32 + (r >> 1) * 16 + (r & 1) * 8 + lr;
 #pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-              float4 bb = make4(0.f);
-              if (a.b1 != nullptr) bb = ldg4(a.b1 + ch0 + j4 * 4);
-              val[j4 * 4 + 0] = fmaxf(val[j4 * 4 + 0] + bb.x, 0.f);
-              val[j4 * 4 + 1] = fmaxf(val[j4 * 4 + 1] + bb.y, 0.f);
-              val[j4 * 4 + 2] = fmaxf(val[j4 * 4 + 2] + bb.z, 0.f);
-              val[j4 * 4 + 3] = fmaxf(val[j4 * 4 + 3] + bb.w, 0.f);
+          for (int c = 0; c < 2; ++c) {
+            float x0 = v[r][c][0], x1 = v[r][c][1];
+            if (pix_mid[r] >= 0) {
+              if (a.mid_mask != nullptr) { x0 = mk[r][c].x > 0.f ? x0 : 0.f; x1 = mk[r][c].y > 0.f ? x1 : 0.f; }
+              else { x0 = fmaxf(x0 + bb[c].x, 0.f); x1 = fmaxf(x1 + bb[c].y, 0.f); }
+            } else { x0 = 0.f; x1 = 0.f; }
+            if (rdec[r] >= 0) {
+              const float h0 = tf32_hi(x0), h1 = tf32_hi(x1);
+              const int col = (ch0 & 31) + 8 * c + lc;                       // channel within the 32-channel slab
+              const uint32_t off = (uint32_t)m * 128 + ((uint32_t)((col >> 2) ^ (m & 7)) << 4) + (uint32_t)(col & 3) * 4;
+              *reinterpret_cast<float2*>(slab_hi + off) = make_float2(h0, h1);
+              *reinterpret_cast<float2*>(slab_hi + off + K::ACT_BYTES) = make_float2(x0 - h0, x1 - h1);
             }
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) val[j] = 0.f;
-        }
-        if (m < M1) {
-          unsigned char* slab_hi = hi_base + (size_t)(ch0 >> 5) * K::SLAB_BYTES;
-          const int cbase = (ch0 & 31) >> 2;
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            float4 hi, lo;
-            split4(make_float4(val[j4 * 4 + 0], val[j4 * 4 + 1], val[j4 * 4 + 2], val[j4 * 4 + 3]), hi, lo);
-            const uint32_t off = sw128_off(m, cbase + j4);
-            *reinterpret_cast<float4*>(slab_hi + off) = hi;
-            *reinterpret_cast<float4*>(slab_hi + off + K::ACT_BYTES) = lo;
+            if (a.mid_out != nullptr && pix_mid[r] >= 0)
+              *reinterpret_cast<float2*>(a.mid_out + img + (size_t)pix_mid[r] * C + ch0 + 8 * c + lc) = make_float2(x0, x1);
           }
         }
         // both halves of every quadrant have written their 16 channels of slab i: the second conv may consume it
         tc_fence_before();
         fence_proxy_async();
         mbar_arrive(bar_midfull + 8 * (b * SLABS + i));
-        if (a.mid_out != nullptr) {
-          // `mid` (fp32, as computed) -> staging -> coalesced global stores (a / c of the forward pass, dc' / da' backward)
-          __syncwarp();
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4)
-            *stg_ptr(stg, lane, j4) = make_float4(val[j4 * 4 + 0], val[j4 * 4 + 1], val[j4 * 4 + 2], val[j4 * 4 + 3]);
-          __syncwarp();
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            const int r = 8 * kk + rsub8;
-            const int pix = __shfl_sync(0xffffffffu, pix_mid, r);
-            if (pix >= 0) *reinterpret_cast<float4*>(a.mid_out + img + (size_t)pix * C + ch0 + c4 * 4) = *stg_ptr(stg, r, c4);
-          }
-        }
       }
       if (tracing && tid == 0) trc[10] += clock64() - te1;
 
       // ================================================== epilogue 2: out = acc2 + biases (+ mask / residual), sums
-      auto fetch_epi = [&](int i) {      // coalesced epilogue inputs of sub-block i -> registers
-        const int ch0 = (2 * i + half) * 16;
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          const int pix = __shfl_sync(0xffffffffu, pix_out, 8 * kk + rsub8);
-          pre[kk] = make4(0.f);
-          pre2[kk] = make4(0.f);
-          if (pix >= 0) {
-            pre[kk] = ldg4(a.e0 + img + (size_t)pix * C + ch0 + c4 * 4);                                // p  |  dy
-            if (a.epi == kEpiBwdResidual) pre2[kk] = ldg4(a.e1 + img + (size_t)pix * C + ch0 + c4 * 4); //    |  y
-          }
-        }
-      };
-      if (a.epi != kEpiFwd) fetch_epi(0);
+      if (a.epi != kEpiFwd) {
+        fetch2(a.e0, pix_out, half * 16, pre);                                  // p  |  dy
+        if (a.epi == kEpiBwdResidual) fetch2(a.e1, pix_out, half * 16, pre2);   //    |  y
+      }
       {
         const long long tw0 = tracing ? clock64() : 0;
         mbar_wait(bar_acc2full + 8 * a2, (it >> 1) & 1);
@@ -606,102 +626,85 @@ pair_tc3_kernel(const __grid_constant__ PairArgs a, const Geo geo) {
         if (tracing && tid == 0) trc[6] += clock64() - tw0;
       }
       const long long te2 = tracing ? clock64() : 0;
-#pragma unroll
+#pragma unroll 1
       for (int i = 0; i < K::NSB; ++i) {
         const int ch0 = (2 * i + half) * 16;
-        float val[16];
-        float ev[16];
+        float v[4][2][2];
+        float2 ev[4][2], ey[4][2];
         if (a.epi != kEpiFwd) {
-          __syncwarp();
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            float4 t4 = pre[kk];
-            if (a.epi == kEpiBwdResidual) {
-              t4.x = pre2[kk].x > 0.f ? t4.x : 0.f; t4.y = pre2[kk].y > 0.f ? t4.y : 0.f;
-              t4.z = pre2[kk].z > 0.f ? t4.z : 0.f; t4.w = pre2[kk].w > 0.f ? t4.w : 0.f;
-            }
-            *stg_ptr(stg, 8 * kk + rsub8, c4) = t4;
-          }
-          __syncwarp();
+          for (int r = 0; r < 4; ++r)
 #pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            const float4 t4 = *stg_ptr(stg, lane, j4);
-            ev[j4 * 4 + 0] = t4.x; ev[j4 * 4 + 1] = t4.y; ev[j4 * 4 + 2] = t4.z; ev[j4 * 4 + 3] = t4.w;
+            for (int c = 0; c < 2; ++c) { ev[r][c] = pre[r][c]; ey[r][c] = pre2[r][c]; }
+          if (i + 1 < K::NSB) {
+            fetch2(a.e0, pix_out, ch0 + 32, pre);
+            if (a.epi == kEpiBwdResidual) fetch2(a.e1, pix_out, ch0 + 32, pre2);
           }
-          if (i + 1 < K::NSB) fetch_epi(i + 1);
         }
-        if (K::NSTACK) tmem_ld16x2(acc2 + lane_addr + ch0, acc2 + lane_addr + C + ch0, val);
-        else tmem_ld16(acc2 + lane_addr + ch0, val);
+        load_acc(acc2, ch0, v);
         if (i == K::NSB - 1) {     // last read of this accumulator: the MMA warp may overwrite it (tile it+2)
           tc_fence_before();
           mbar_arrive(bar_acc2free + 8 * a2);
         }
+        float s1[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, s2[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
 #pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) {
-          float4 bb = make4(0.f);
-          if (a.b2 != nullptr) bb = ldg4(a.b2 + ch0 + j4 * 4);
-          if (a.bad != nullptr) {
-            const float4 b3 = ldg4(a.bad + ch0 + j4 * 4);
-            bb.x += b3.x; bb.y += b3.y; bb.z += b3.z; bb.w += b3.w;
+        for (int c = 0; c < 2; ++c) {
+          const int chc = ch0 + 8 * c + lc;
+          float2 bb = make_float2(0.f, 0.f);
+          if (a.b2 != nullptr) bb = __ldg(reinterpret_cast<const float2*>(a.b2 + chc));
+          if (a.bad != nullptr) { const float2 b3 = __ldg(reinterpret_cast<const float2*>(a.bad + chc)); bb.x += b3.x; bb.y += b3.y; }
+          float2 sc = make_float2(0.f, 0.f), sh = sc, mean = sc, istd = sc;
+          if (a.epi == kEpiBwdMaskStats) {
+            mean = __ldg(reinterpret_cast<const float2*>(a.e_stats + chc));
+            istd = __ldg(reinterpret_cast<const float2*>(a.e_stats + C + chc));
+            sc = __ldg(reinterpret_cast<const float2*>(a.e_stats + 2 * C + chc));
+            sh = __ldg(reinterpret_cast<const float2*>(a.e_stats + 3 * C + chc));
           }
-          val[j4 * 4 + 0] += bb.x; val[j4 * 4 + 1] += bb.y; val[j4 * 4 + 2] += bb.z; val[j4 * 4 + 3] += bb.w;
-        }
-        float w2[16];   // second statistic's per-element factor
-        if (a.epi == kEpiBwdMaskStats) {
 #pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            const float4 sc = ldg4(a.e_stats + 2 * C + ch0 + j4 * 4), sh = ldg4(a.e_stats + 3 * C + ch0 + j4 * 4);
-            const float4 mean = ldg4(a.e_stats + ch0 + j4 * 4), istd = ldg4(a.e_stats + C + ch0 + j4 * 4);
-            const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
-            const float mnv[4] = {mean.x, mean.y, mean.z, mean.w}, isv[4] = {istd.x, istd.y, istd.z, istd.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float pv = ev[j4 * 4 + e];
-              val[j4 * 4 + e] = fmaf(pv, scv[e], shv[e]) > 0.f ? val[j4 * 4 + e] : 0.f;
-              w2[j4 * 4 + e] = (pv - mnv[e]) * isv[e];
+          for (int r = 0; r < 4; ++r) {
+            float x0 = v[r][c][0] + bb.x, x1 = v[r][c][1] + bb.y;
+            float w0 = 0.f, w1 = 0.f;      // second statistic's per-element factor
+            if (a.epi == kEpiBwdMaskStats) {
+              x0 = fmaf(ev[r][c].x, sc.x, sh.x) > 0.f ? x0 : 0.f;
+              x1 = fmaf(ev[r][c].y, sc.y, sh.y) > 0.f ? x1 : 0.f;
+              w0 = (ev[r][c].x - mean.x) * istd.x;
+              w1 = (ev[r][c].y - mean.y) * istd.y;
+            } else if (a.epi == kEpiBwdResidual) {
+              x0 += ey[r][c].x > 0.f ? ev[r][c].x : 0.f;
+              x1 += ey[r][c].y > 0.f ? ev[r][c].y : 0.f;
+            }
+            if (pix_out[r] >= 0) {
+              *reinterpret_cast<float2*>(a.out + img + (size_t)pix_out[r] * C + chc) = make_float2(x0, x1);
+              s1[c][0] += x0; s1[c][1] += x1;
+              if (a.epi == kEpiFwd) { s2[c][0] = fmaf(x0, x0, s2[c][0]); s2[c][1] = fmaf(x1, x1, s2[c][1]); }
+              else { s2[c][0] = fmaf(x0, w0, s2[c][0]); s2[c][1] = fmaf(x1, w1, s2[c][1]); }
             }
           }
-        } else if (a.epi == kEpiBwdResidual) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) val[j] += ev[j];
         }
-        if (!out_valid) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) val[j] = 0.f;
-        }
-        // ---- results -> staging -> coalesced global stores
-        __syncwarp();
-#pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4)
-          *stg_ptr(stg, lane, j4) = make_float4(val[j4 * 4 + 0], val[j4 * 4 + 1], val[j4 * 4 + 2], val[j4 * 4 + 3]);
-        __syncwarp();
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          const int r = 8 * kk + rsub8;
-          const int pix = __shfl_sync(0xffffffffu, pix_out, r);
-          if (pix >= 0) *reinterpret_cast<float4*>(a.out + img + (size_t)pix * C + ch0 + c4 * 4) = *stg_ptr(stg, r, c4);
-        }
-        // ---- per-channel sums of this warp's 32 rows (register butterfly), kept across tiles
+        // ---- per-channel sums over this warp's 32 rows: the 8 lanes with the same (lane & 3) own the same columns
         if (a.sums != nullptr) {
-          float t1[16], t2[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            t1[j] = val[j];
-            t2[j] = a.epi == kEpiFwd ? val[j] * val[j] : val[j] * w2[j];
-          }
-          s1acc[i] += butterfly16(t1, lane);
-          s2acc[i] += butterfly16(t2, lane);
+          for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              float t1 = s1[c][e], t2 = s2[c][e];
+#pragma unroll
+              for (int o = 4; o < 32; o <<= 1) {
+                t1 += __shfl_xor_sync(0xffffffffu, t1, o);
+                t2 += __shfl_xor_sync(0xffffffffu, t2, o);
+              }
+              if (lr == 0) {
+                atomicAdd(ssum + ch0 + 8 * c + lc + e, t1);
+                atomicAdd(ssum + C + ch0 + 8 * c + lc + e, t2);
+              }
+            }
         }
       }
       if (tracing && tid == 0) trc[11] += clock64() - te2;
     }
-    if (a.sums != nullptr && (lane & 1) == 0) {
-#pragma unroll
-      for (int i = 0; i < K::NSB; ++i) {
-        const int ch = (2 * i + half) * 16 + sumch;
-        atomicAdd(a.sums + ch, (double)s1acc[i]);
-        atomicAdd(a.sums + C + ch, (double)s2acc[i]);
-      }
+    if (a.sums != nullptr) {
+      named_bar_sync(1, N_EPI);
+      for (int i = tid; i < 2 * C; i += N_EPI) atomicAdd(a.sums + i, (double)ssum[i]);
     }
   }
 

@@ -723,10 +723,14 @@ pair_tc3_kernel(const __grid_constant__ PairArgs a, const Geo geo) {
   }
 }
 
+// Lattice tile (TU x TV mid pixels of TR residue classes, <= 128 mid rows, <= IN_MAX input rows) that needs the fewest
+// rounds of the persistent grid, then the fewest tiles, then the smallest input tile.  Residue classes may be batched
+// (TR > 1) whatever part of the class lattice the tile covers: for d = 8 at 64x128 (an 8 x 16 lattice per class) two
+// classes x 8 x 6 fill a tile where one class x 8 x 14 leaves every second tile almost empty.
 template <int C>
-TileShape choose_tile(int Ul, int Vl, int d) {
+TileShape choose_tile(int Ul, int Vl, int d, int nimg) {
   TileShape best{1, 2, 1};
-  long best_ctas = -1, best_load = 0;
+  long best_rounds = -1, best_tiles = 0, best_load = 0;
   for (int TR = 1; TR <= 8; ++TR) {
     if (TR > d * d) break;
     for (int TU = 1; TU <= 32; ++TU) {
@@ -734,11 +738,11 @@ TileShape choose_tile(int Ul, int Vl, int d) {
         const int TVH = TV + 2;
         if (TR * TU * TVH > 128) break;
         if (TR * (TU + 2) * TVH > IN_MAX) break;
-        if (TR > 1 && (TU < Ul || TV < Vl)) continue;
-        const long ctas = (long)cdiv(d * d, TR) * cdiv(Ul, TU) * cdiv(Vl, TV);
+        const long tiles = (long)nimg * cdiv(d * d, TR) * cdiv(Ul, TU) * cdiv(Vl, TV);
+        const long rounds = (tiles + kNumSMs - 1) / kNumSMs;
         const long load = (long)TR * (TU + 2) * TVH;
-        if (best_ctas < 0 || ctas < best_ctas || (ctas == best_ctas && load < best_load)) {
-          best_ctas = ctas; best_load = load; best = TileShape{TU, TV, TR};
+        if (best_rounds < 0 || rounds < best_rounds || (rounds == best_rounds && (tiles < best_tiles || (tiles == best_tiles && load < best_load)))) {
+          best_rounds = rounds; best_tiles = tiles; best_load = load; best = TileShape{TU, TV, TR};
         }
       }
     }
@@ -763,7 +767,7 @@ int launch_c(const PairArgs& a, cudaStream_t s) {
   const int d = a.dil;
   const int U = a.vert_first ? a.H : a.W, V = a.vert_first ? a.W : a.H;
   const int Ul = cdiv(U, d), Vl = cdiv(V, d);
-  const TileShape ts = choose_tile<C>(Ul, Vl, d);
+  const TileShape ts = choose_tile<C>(Ul, Vl, d, a.N);
   const long total = (long)a.N * cdiv(d * d, ts.TR) * cdiv(Ul, ts.TU) * cdiv(Vl, ts.TV);
   MDIL_REQUIRE(total > 0 && total < (1L << 30), "pair_tc3: tile count");
   MDIL_REQUIRE(a.wstream_tc != nullptr && ((uintptr_t)a.wstream_tc & 15) == 0, "pair_tc3: weight stream");

@@ -136,7 +136,7 @@ __device__ __forceinline__ void split_tf32_c(float x, uint32_t& hi, uint32_t& lo
 }
 constexpr int CM_WP = 18;   // shared-memory weight row pitch (floats)
 
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 3)
 conv_mma_kernel(const __grid_constant__ ConvGeom g, const float* __restrict__ A, const float* __restrict__ Wp,
                 const float* __restrict__ bias, float* __restrict__ out, int tiles_per_cta) {
   extern __shared__ __align__(16) float wsm[];   // [total taps][CIN][CM_WP]
@@ -293,7 +293,7 @@ static int conv_mma_launch(const ConvGeom& g, const float* A, const float* Wp, c
   const int coblocks = cdiv(g.COUT, 16);
   // persistent-ish: ~4 CTAs per SM in total, each walking tiles_per_cta groups of 8 warp tiles
   size_t groups = (ntiles + 7) / 8;
-  int want = cdiv(4 * kNumSMs, coblocks);
+  int want = cdiv(6 * kNumSMs, coblocks);
   int tpc = (int)((groups + want - 1) / want);
   if (tpc < 1) tpc = 1;
   dim3 grid((unsigned)((groups + tpc - 1) / tpc), (unsigned)coblocks);
@@ -619,7 +619,7 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
 }
 
 template <int NTL, int TAPS>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, NTL <= 2 ? 3 : 2)
 wgrad_mma_kernel(const __grid_constant__ ConvGeom g, const __grid_constant__ MmaPlan plan, const float* __restrict__ A,
                  const float* __restrict__ a_scale, const float* __restrict__ a_shift, const float* __restrict__ G,
                  float* __restrict__ dW, long s_ci, long s_co, long s_t, float* __restrict__ db, int pixels_per_cta) {
@@ -772,7 +772,7 @@ static int wgrad_mma_launch(const ConvGeom& g, const float* A, const float* a_sc
     }
   const int zb = cdiv(g.CIN, 16) * cdiv(g.COUT, 8 * NTL);
   const size_t P = (size_t)g.N * g.VH * g.VW;
-  int want = cdiv(2 * kNumSMs, plan.npass * zb);
+  int want = cdiv((NTL <= 2 ? 3 : 2) * kNumSMs, plan.npass * zb);    // one wave of co-resident CTAs
   if (want < 1) want = 1;
   size_t ppc = (P + want - 1) / want;
   ppc = (ppc + 63) / 64 * 64;

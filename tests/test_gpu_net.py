@@ -205,3 +205,19 @@ def test_full_size_train_step_runs_and_decreases_loss():
     losses = [float(tr.step(x, labels)) for _ in range(6)]
     assert all(np.isfinite(losses))
     assert losses[-1] < losses[0]
+
+
+def test_device_prefetcher_round_trip():
+    """mdil_ss_b200.data.DevicePrefetcher: the batch handed back is the batch that was put (copied on a side stream)."""
+    from mdil_ss_b200.data import DevicePrefetcher
+    pf = DevicePrefetcher(DEV)
+    g = torch.Generator().manual_seed(5)
+    for _ in range(3):
+        x = torch.rand(2, 3, 64, 128, generator=g).pin_memory()
+        y = torch.randint(0, 20, (2, 1, 64, 128), generator=g).pin_memory()
+        pf.put(x, y)
+        xd, yd = pf.get()
+        torch.cuda.synchronize()
+        assert torch.equal(xd.cpu(), x) and torch.equal(yd.cpu(), y)
+    with pytest.raises(RuntimeError):
+        pf.get()

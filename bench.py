@@ -33,7 +33,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="step1", choices=["step1", "step2"])
+    ap.add_argument("--workload", default="step1", choices=["step1", "step2", "step3"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="crops per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ncu-step", action="store_true",
@@ -46,8 +46,11 @@ def workload_name(args):
     if args.workload == "step1":
         return (f"Step-1 CS single-domain train (fwd+CE2d+bwd+allreduce+Adam), 20 cls, batch {args.batch}/GPU, "
                 f"{H}x{W} synthetic")
-    return (f"Step-2 CS->BDD train (student fwd x2 + teacher fwd, CE2d + 0.1*KD, bwd, allreduce, Adam), 20/20 cls, "
-            f"batch {args.batch}/GPU, {H}x{W} synthetic")
+    if args.workload == "step2":
+        return (f"Step-2 CS->BDD train (student fwd x2 + teacher fwd, CE2d + 0.1*KD, bwd, allreduce, Adam), 20/20 cls, "
+                f"batch {args.batch}/GPU, {H}x{W} synthetic")
+    return (f"Step-3 CS|BDD->IDD train (CE step, then student fwd x2 + teacher fwd x2 + 0.1*(KD+KD) step: two "
+            f"all-reduce + Adam per iteration), 20/20/27 cls, batch {args.batch}/GPU, {H}x{W} synthetic")
 
 
 # ------------------------------------------------------------------------------------------- clocks
@@ -101,8 +104,9 @@ def oracle_step_factory(workload, n):
     from oracle import erfnet_rap_oracle as oracle
     g = torch.Generator().manual_seed(1234)
     images = torch.rand(n, 3, H, W, generator=g)
-    labels = torch.randint(0, NCLS, (n, 1, H // 32, W // 32), generator=g).repeat_interleave(32, 2).repeat_interleave(32, 3)
-    weight = torch.tensor(oracle.WEIGHT_CITY if workload == "step1" else oracle.WEIGHT_BDD)
+    labels = torch.randint(0, 27 if workload == "step3" else NCLS, (n, 1, H // 32, W // 32),
+                           generator=g).repeat_interleave(32, 2).repeat_interleave(32, 3)
+    weight = torch.tensor({"step1": oracle.WEIGHT_CITY, "step2": oracle.WEIGHT_BDD, "step3": oracle.WEIGHT_IDD}[workload])
     if workload == "step1":
         sd = oracle.init_state_dict([NCLS], 1, seed=0)
         state = [dict() for _ in oracle.param_names(sd)]
@@ -112,6 +116,16 @@ def oracle_step_factory(workload, n):
             noise = oracle.make_dropout_noise(n, True)
             loss, _, _ = oracle.step1_iteration(sd, images, labels, weight, 0, noise, state)
             return float(loss)
+    elif workload == "step3":
+        sd_old = oracle.init_state_dict([NCLS, NCLS], 2, seed=0)
+        sd = oracle.init_state_dict([NCLS, NCLS, 27], 3, seed=1)
+        state = {}
+
+        def step():
+            torch.manual_seed(7)
+            noises = [oracle.make_dropout_noise(n, True) for _ in range(5)]
+            ce, kd, _, _, _ = oracle.step3_iteration(sd, sd_old, images, labels, weight, 2, 0.1, noises, state)
+            return float(ce) + float(kd)
     else:
         sd_old = oracle.init_state_dict([NCLS], 1, seed=0)
         sd = oracle.init_state_dict([NCLS, NCLS], 2, seed=1)
@@ -193,19 +207,28 @@ def run_ours(args):
     with contextlib.redirect_stdout(io.StringIO()):
         if args.workload == "step1":
             model = Net([NCLS], 1, 0).to(dev)
-        else:
+        elif args.workload == "step2":
             model_old = Net([NCLS], 1, 0).to(dev)
             model = Net([NCLS, NCLS], 2, 1).to(dev)
+        else:
+            model_old = Net([NCLS, NCLS], 2, 1).to(dev)
+            model = Net([NCLS, NCLS, 27], 3, 2).to(dev)
     broadcast_module(model)
+    ncls_labels = NCLS
     if args.workload == "step1":
         trainer = Step1Trainer(model, class_weights("cityscapes", dev))
-    else:
+    elif args.workload == "step2":
         broadcast_module(model_old)
         trainer = Step2Trainer(model, model_old, class_weights("BDD", dev), 1, 0.1)
+    else:
+        from mdil_ss_b200.train_step import Step3Trainer
+        broadcast_module(model_old)
+        trainer = Step3Trainer(model, model_old, class_weights("IDD", dev), 2, 0.1)
+        ncls_labels = 27
 
     g = torch.Generator().manual_seed(1234 + rank)
     images_h = torch.rand(n, 3, H, W, generator=g).pin_memory()
-    labels_h = (torch.randint(0, NCLS, (n, 1, H // 32, W // 32), generator=g)
+    labels_h = (torch.randint(0, ncls_labels, (n, 1, H // 32, W // 32), generator=g)
                 .repeat_interleave(32, 2).repeat_interleave(32, 3).contiguous().pin_memory())
     images = images_h.to(dev, non_blocking=True)
     labels = labels_h.to(dev, non_blocking=True)

@@ -125,13 +125,34 @@ class FlatAdam:
         b1, b2 = self.betas
         for g in self.groups:
             buf = g["buf"]
+            steps = g.setdefault("steps", [0] * len(buf.params))
             if buf.data.is_cuda:
+                # torch.optim.Adam skips parameters whose .grad is None, which is what the drivers' zero_grad() leaves
+                # behind for tensors no loss reached (step 3's KD step never touches the new domain's tensors,
+                # train_new_task_step3.py:349-353): a parameter whose gradient was not written since zero_grad()
+                # (functional.grad_target clears `_mdil_grad_fresh` on the first write) keeps its value, moments and
+                # step count.  Contiguous runs of updated parameters with the same step count share one fused launch.
+                touched = [not getattr(p, "_mdil_grad_fresh", False) for p in buf.params]
+                i, n = 0, len(buf.params)
                 with torch.cuda.device_of(buf.data):
-                    L.check(L.lib().mdil_adam_step(buf.data.data_ptr(), buf.grad.data_ptr(), g["exp_avg"].data_ptr(),
-                                                   g["exp_avg_sq"].data_ptr(), buf.numel(), g["lr"], b1, b2, self.eps,
-                                                   self.weight_decay, self.step_count, scale,
-                                                   torch.cuda.current_stream().cuda_stream), "mdil_adam_step")
+                    while i < n:
+                        if not touched[i]:
+                            i += 1
+                            continue
+                        j = i
+                        while j + 1 < n and touched[j + 1] and steps[j + 1] == steps[i]:
+                            j += 1
+                        lo, hi = buf.offsets[i], buf.offsets[j + 1]
+                        L.check(L.lib().mdil_adam_step(buf.data.data_ptr() + 4 * lo, buf.grad.data_ptr() + 4 * lo,
+                                                       g["exp_avg"].data_ptr() + 4 * lo, g["exp_avg_sq"].data_ptr() + 4 * lo,
+                                                       hi - lo, g["lr"], b1, b2, self.eps, self.weight_decay, steps[i] + 1,
+                                                       scale, torch.cuda.current_stream().cuda_stream), "mdil_adam_step")
+                        for k in range(i, j + 1):
+                            steps[k] += 1
+                        i = j + 1
             else:
+                for k in range(len(steps)):
+                    steps[k] += 1
                 with torch.no_grad():
                     grad = buf.grad * scale + self.weight_decay * buf.data
                     g["exp_avg"].mul_(b1).add_(grad, alpha=1 - b1)

@@ -302,6 +302,49 @@ def step2_iteration(sd: SD, sd_old: SD, images: torch.Tensor, labels: torch.Tens
     return ce.detach(), kd.detach(), out_t.detach(), gdict
 
 
+def step3_iteration(sd: SD, sd_old: SD, images: torch.Tensor, labels: torch.Tensor, weight: torch.Tensor,
+                    task: int = 2, lambdac: float = 0.1, noises=None, opt_state: Optional[dict] = None,
+                    lr_scale: float = 1.0):
+    """One iteration of train_new_task_step3.py:301-356: student fwd(t) -> CE -> backward -> optimiser step; then
+    student fwd(t-1), fwd(t-2) and teacher fwd(t-1), fwd(t-2) (the teacher is never put in eval mode, :301),
+    lambda * (KD_{t-1} + KD_{t-2}) -> backward -> second optimiser step.  ``noises`` = the five Dropout2d streams in
+    call order.  As torch.optim.Adam does after ``zero_grad()`` (grads set to None), parameters that receive no
+    gradient in the KD step (the domain-t tensors) are left untouched by the second step.
+    Returns (ce, kd, logits_t, CE-step grads by name, KD-step grads by name)."""
+    noises = noises if noises is not None else [None] * 5
+    names = trainable_names_incremental(sd, task)
+    shared = [n for n in names if is_shared(n)]
+    ds = [n for n in names if is_ds_curr(n, task)]
+    state = opt_state if opt_state is not None else {}
+    for n in names:
+        state.setdefault(n, {})
+
+    def update(gdict):
+        with torch.no_grad():
+            sh = [n for n in shared if n in gdict]
+            dd = [n for n in ds if n in gdict]
+            adam_step([sd[n] for n in sh], [gdict[n] for n in sh], [state[n] for n in sh], 5e-6 * lr_scale)
+            adam_step([sd[n] for n in dd], [gdict[n] for n in dd], [state[n] for n in dd], 5e-4 * lr_scale)
+
+    work = _with_grad(sd, names)
+    out_t = net_forward(work, images, task, True, noises[0])
+    ce = cross_entropy2d(out_t, labels[:, 0], weight)
+    grads = torch.autograd.grad(ce, [work[n] for n in names], allow_unused=True)
+    g_ce = {n: g for n, g in zip(names, grads) if g is not None}
+    update(g_ce)
+    work = _with_grad(sd, names)
+    out_p1 = net_forward(work, images, task - 1, True, noises[1])
+    out_p0 = net_forward(work, images, task - 2, True, noises[2])
+    with torch.no_grad():
+        old_p1 = net_forward(sd_old, images, task - 1, True, noises[3])
+        old_p0 = net_forward(sd_old, images, task - 2, True, noises[4])
+    kd = lambdac * (kd_loss(out_p1, old_p1) + kd_loss(out_p0, old_p0))
+    grads = torch.autograd.grad(kd, [work[n] for n in names], allow_unused=True)
+    g_kd = {n: g for n, g in zip(names, grads) if g is not None}
+    update(g_kd)
+    return ce.detach(), kd.detach(), out_t.detach(), g_ce, g_kd
+
+
 # ------------------------------------------------------- constructor restatement
 def init_state_dict(num_classes: Sequence[int] = (20,), nb_tasks: int = 1, seed: Optional[int] = None) -> SD:
     """Restates Net.__init__ (models/erfnet_RA_parallel.py:195-205 and the block constructors :14-19, :68-88,

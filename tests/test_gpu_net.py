@@ -207,6 +207,53 @@ def test_full_size_train_step_runs_and_decreases_loss():
     assert losses[-1] < losses[0]
 
 
+def test_step3_iteration_matches_reference():
+    """One CS|BDD -> IDD iteration (train_new_task_step3.py:301-356: CE step + KD step, two optimiser steps) against
+    the fixture generated by the unmodified reference (tests/golden/make_golden_step3.py)."""
+    from mdil_ss_b200.train_step import Step3Trainer
+    g = golden("step3_iter.npz")
+    sd_new = make_sd([20, 20, 27], 20, 24)
+    teacher = _net([20, 20], make_sd([20, 20], 19, 23))
+    student = _net([20, 20, 27], sd_new)
+    gen = torch.Generator().manual_seed(500)
+    x = torch.rand(2, 3, 32, 64, generator=gen).to(DEV)
+    labels = torch.randint(0, 27, (2, 1, 32, 64), generator=gen).to(DEV)
+    tr = Step3Trainer(student, teacher, torch.tensor(oracle.WEIGHT_IDD, device=DEV), 2, 0.1)
+    streams = [_to_dev(noise_list(g, f"noise{s}_")) for s in range(5)]
+    calls = []
+
+    def wrap(net, tag, first):
+        orig = net.forward
+
+        def fwd(inp, task, drop_noise=None):
+            calls.append((tag, task))
+            return orig(inp, task, drop_noise=streams[first + sum(1 for c in calls if c[0] == tag) - 1])
+
+        net.forward = fwd
+
+    wrap(student, "s", 0)     # student draws streams 0, 1, 2
+    wrap(teacher, "t", 3)     # teacher (left in train mode, as the reference does) draws streams 3, 4
+    ce, kd = tr.step(x, labels)
+    assert calls == [("s", 2), ("s", 1), ("s", 0), ("t", 1), ("t", 0)]
+    assert abs(float(ce) - float(g["ce"])) <= TOL * abs(float(g["ce"]))
+    assert abs(float(kd) - float(g["kd"])) <= TOL * abs(float(g["kd"]))
+    # gradients left by the KD step (shared encoder convolutions only)
+    names_kd = [str(s) for s in g["grad_names_kd"]]
+    grads = dict(student.named_parameters())
+    gabs = np.array([float(grads[n].grad.double().abs().sum()) for n in names_kd])
+    np.testing.assert_allclose(gabs, g["grad_abs_kd"], rtol=5e-2, atol=1e-6)
+    # post-iteration parameters (both optimiser steps; the domain-2 tensors must not move in the KD step)
+    gref = dict(zip([str(s) for s in g["grad_names"]], g["grad_abs_ce"]))
+    after = student.state_dict()
+    for k, ref_delta in zip([str(s) for s in g["after_names"]], g["delta_abs"]):
+        if "running" in k or "num_batches" in k:
+            continue
+        if k in gref and gref[k] < 1e-3:      # mathematically-zero gradients: Adam's first update is rounding noise
+            continue
+        d = float((after[k].double().cpu() - sd_new[k].double()).abs().sum())
+        assert abs(d - ref_delta) <= 6e-2 * ref_delta + 1e-6, f"{k}: |delta| {d} vs reference {ref_delta}"
+
+
 def test_device_prefetcher_round_trip():
     """mdil_ss_b200.data.DevicePrefetcher: the batch handed back is the batch that was put (copied on a side stream)."""
     from mdil_ss_b200.data import DevicePrefetcher

@@ -110,3 +110,27 @@ def test_step2_iteration_fixture():
     np.testing.assert_allclose(gabs, g["grad_abs"], rtol=5e-4, atol=2e-5)
     after = np.array([float(sd[str(k)].double().sum()) for k in g["after_names"]])
     np.testing.assert_allclose(after, g["after_sum"], rtol=1e-5, atol=2e-4)
+
+
+def test_step3_iteration_fixture():
+    """tests/golden/make_golden_step3.py: one CS|BDD -> IDD iteration of the unmodified reference (two optimiser steps)."""
+    g = golden("step3_iter.npz")
+    sd_old = make_sd([20, 20], 19, 23)
+    sd = make_sd([20, 20, 27], 20, 24)
+    sd0 = oracle.clone_sd(sd)
+    gen = torch.Generator().manual_seed(500)
+    x = torch.rand(2, 3, 32, 64, generator=gen)
+    labels = torch.randint(0, 27, (2, 1, 32, 64), generator=gen)
+    noises = [noise_list(g, f"noise{s}_") for s in range(5)]
+    ce, kd, out_t, g_ce, g_kd = oracle.step3_iteration(sd, sd_old, x, labels, torch.tensor(oracle.WEIGHT_IDD), 2, 0.1, noises)
+    assert abs(float(ce) - float(g["ce"])) <= 1e-5 * abs(float(g["ce"]))
+    assert abs(float(kd) - float(g["kd"])) <= 1e-4 * abs(float(g["kd"]))
+    assert_close(out_t, torch.from_numpy(g["out"]), TOL, "out")
+    names = [str(s) for s in g["grad_names"]]
+    assert sorted(names) == sorted(g_ce.keys())
+    np.testing.assert_allclose(np.array([float(g_ce[n].double().abs().sum()) for n in names]), g["grad_abs_ce"], rtol=5e-4, atol=2e-5)
+    names_kd = [str(s) for s in g["grad_names_kd"]]
+    assert sorted(names_kd) == sorted(g_kd.keys())
+    np.testing.assert_allclose(np.array([float(g_kd[n].double().abs().sum()) for n in names_kd]), g["grad_abs_kd"], rtol=2e-3, atol=2e-6)
+    delta = np.array([float((sd[str(k)].double() - sd0[str(k)].double()).abs().sum()) for k in g["after_names"]])
+    np.testing.assert_allclose(delta, g["delta_abs"], rtol=2e-3, atol=2e-4)

@@ -393,7 +393,7 @@ class CrossEntropy2dFn(torch.autograd.Function):
     One fused pass produces the loss and the (unnormalised) logit gradient."""
 
     @staticmethod
-    def forward(ctx, logits, target, weight):
+    def forward(ctx, logits, target, weight, group_norm=None):
         _require_cuda(logits, "cross_entropy2d")
         lib = L.lib()
         logits = logits.contiguous()
@@ -413,6 +413,17 @@ class CrossEntropy2dFn(torch.autograd.Function):
             dlogits = torch.empty_like(logits) if need else None
             L.check(lib.mdil_ce2d_fwd_bwd(logits.data_ptr(), target.data_ptr(), weight.data_ptr(), n, c, h, w,
                                           loss.data_ptr(), acc.data_ptr(), _ptr(dlogits), _stream()), "mdil_ce2d_fwd_bwd")
+            ctx.world = 1
+            if group_norm is not None:
+                # nn.DataParallel computes the loss on the gathered logits: sum(w*nll) / sum(w) over the GLOBAL batch
+                # (SURVEY 8e).  One all-reduce of the two fp64 accumulators makes every rank return that value and
+                # scale its logit gradient by world / sum_global(w) (the optimiser averages the ranks' gradients).
+                import torch.distributed as dist
+                if dist.is_available() and dist.is_initialized() and dist.get_world_size(group_norm or None) > 1:
+                    grp = group_norm or None
+                    dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=grp)
+                    ctx.world = dist.get_world_size(grp)
+                    loss = (acc[0] / acc[1]).to(torch.float32)
         ctx.internal = (dlogits, acc)
         return loss
 
@@ -421,13 +432,13 @@ class CrossEntropy2dFn(torch.autograd.Function):
         lib = L.lib()
         dlogits, acc = ctx.internal
         if dlogits is None:
-            return None, None, None
+            return None, None, None, None
         ctx.internal = (None, None)  # single use: the stash is scaled in place
         with torch.cuda.device_of(dlogits):
-            g = grad_out.to(dtype=torch.float32).contiguous()
+            g = (grad_out.to(dtype=torch.float32) * float(ctx.world)).contiguous()
             L.check(lib.mdil_ce2d_scale(dlogits.data_ptr(), dlogits.numel(), acc.data_ptr(), g.data_ptr(), _stream()),
                     "mdil_ce2d_scale")
-        return dlogits, None, None
+        return dlogits, None, None, None
 
 
 class OutputKDFn(torch.autograd.Function):

@@ -15,12 +15,18 @@ from . import functional as F_
 
 
 class CrossEntropyLoss2d(torch.nn.Module):
-    def __init__(self, weight=None):
+    """``global_norm=True`` (one process per GPU only): normalise by the class-weight sum of the GLOBAL batch, as
+    nn.DataParallel's loss on the gathered logits does (train_new_task_step2.py:293,474), instead of each rank's own
+    sum — one all-reduce of two fp64 scalars.  ``group`` = the torch.distributed group (default: world)."""
+
+    def __init__(self, weight=None, global_norm: bool = False, group=None):
         super().__init__()
         self.register_buffer("weight", None if weight is None else torch.as_tensor(weight, dtype=torch.float32))
+        self.global_norm, self.group = bool(global_norm), group
 
     def forward(self, outputs, targets):
-        return F_.CrossEntropy2dFn.apply(outputs, targets, self.weight)
+        gn = None if not self.global_norm else (self.group if self.group is not None else False)
+        return F_.CrossEntropy2dFn.apply(outputs, targets, self.weight, gn)
 
 
 FusedCrossEntropyLoss2d = CrossEntropyLoss2d

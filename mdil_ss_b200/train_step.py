@@ -78,7 +78,7 @@ class Step1Trainer:
 
     def __init__(self, model, weight: torch.Tensor, task: int = 0, lr: float = 5e-4):
         self.model, self.task = model, task
-        self.criterion = CrossEntropyLoss2d(weight).to(weight.device)
+        self.criterion = CrossEntropyLoss2d(weight, global_norm=True).to(weight.device)   # DataParallel's global sum(w)
         self.optimizer = FlatAdam([{"params": list(model.parameters())}], lr)
 
     def step(self, images: torch.Tensor, labels: torch.Tensor):
@@ -100,7 +100,7 @@ class Step2Trainer:
         for p in model_old.parameters():
             p.requires_grad = False
         apply_incremental_freeze(model, task)
-        self.criterion = CrossEntropyLoss2d(weight).to(weight.device)
+        self.criterion = CrossEntropyLoss2d(weight, global_norm=True).to(weight.device)   # DataParallel's global sum(w)
         self.kd = OutputKD()
         self.optimizer = FlatAdam(incremental_param_groups(model, task), 5e-4)
 
@@ -129,7 +129,7 @@ class Step3Trainer:
         for p in model_old.parameters():
             p.requires_grad = False
         apply_incremental_freeze(model, task)
-        self.criterion = CrossEntropyLoss2d(weight).to(weight.device)
+        self.criterion = CrossEntropyLoss2d(weight, global_norm=True).to(weight.device)   # DataParallel's global sum(w)
         self.kd = OutputKD()
         self.optimizer = FlatAdam(incremental_param_groups(model, task), 5e-4)
 

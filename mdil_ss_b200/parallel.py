@@ -153,15 +153,57 @@ class FlatAdam:
             else:
                 for k in range(len(steps)):
                     steps[k] += 1
+                t = steps[0]
                 with torch.no_grad():
                     grad = buf.grad * scale + self.weight_decay * buf.data
                     g["exp_avg"].mul_(b1).add_(grad, alpha=1 - b1)
                     g["exp_avg_sq"].mul_(b2).addcmul_(grad, grad, value=1 - b2)
-                    bc1 = 1 - b1 ** self.step_count
-                    bc2 = 1 - b2 ** self.step_count
+                    bc1 = 1 - b1 ** t
+                    bc2 = 1 - b2 ** t
                     denom = (g["exp_avg_sq"].sqrt() / math.sqrt(bc2)).add_(self.eps)
                     buf.data.addcdiv_(g["exp_avg"], denom, value=-g["lr"] / bc1)
         self._bump_versions()
+
+    # ---- torch.optim.Adam's checkpoint format (the drivers save optimizer.state_dict(), train_new_task_step2.py:380)
+    def state_dict(self) -> dict:
+        state, groups, idx = {}, [], 0
+        for g in self.groups:
+            buf = g["buf"]
+            steps = g.get("steps", [0] * len(buf.params))
+            ids = []
+            for k, (o, n, p) in enumerate(zip(buf.offsets, buf.sizes, buf.params)):
+                if steps[k] > 0:
+                    state[idx] = {"step": torch.tensor(float(steps[k])),
+                                  "exp_avg": g["exp_avg"][o:o + n].view(p.shape).clone(),
+                                  "exp_avg_sq": g["exp_avg_sq"][o:o + n].view(p.shape).clone()}
+                ids.append(idx)
+                idx += 1
+            groups.append({"lr": g["lr"], "initial_lr": g["initial_lr"], "betas": tuple(self.betas), "eps": self.eps,
+                           "weight_decay": self.weight_decay, "amsgrad": False, "params": ids})
+        return {"state": state, "param_groups": groups}
+
+    def load_state_dict(self, sd: dict) -> None:
+        if len(sd["param_groups"]) != len(self.groups):
+            raise ValueError("FlatAdam.load_state_dict: parameter group count differs")
+        for g, sg in zip(self.groups, sd["param_groups"]):
+            buf = g["buf"]
+            if len(sg["params"]) != len(buf.params):
+                raise ValueError("FlatAdam.load_state_dict: parameter count of a group differs")
+            g["lr"] = sg["lr"]
+            g["initial_lr"] = sg.get("initial_lr", g["initial_lr"])
+            steps = g.setdefault("steps", [0] * len(buf.params))
+            with torch.no_grad():
+                for k, (o, n, pid) in enumerate(zip(buf.offsets, buf.sizes, sg["params"])):
+                    st = sd["state"].get(pid)
+                    if st is None:
+                        steps[k] = 0
+                        g["exp_avg"][o:o + n].zero_()
+                        g["exp_avg_sq"][o:o + n].zero_()
+                    else:
+                        steps[k] = int(float(st["step"]))
+                        g["exp_avg"][o:o + n].copy_(st["exp_avg"].reshape(-1))
+                        g["exp_avg_sq"][o:o + n].copy_(st["exp_avg_sq"].reshape(-1))
+        self.step_count = max([max(g.get("steps", [0]) or [0]) for g in self.groups] or [0])
 
     def _bump_versions(self) -> None:
         # the parameters changed in place through the flat buffer: bump the version counters that the

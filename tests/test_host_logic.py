@@ -107,3 +107,77 @@ def test_iou_bookkeeping_matches_reference_metric():
     m, per = ev.getIoU()
     m2, per2 = oracle.iou_from_counts(tp, fp, fn)
     assert torch.equal(per, per2) and float(m) == float(m2)
+
+
+def test_flat_adam_state_dict_round_trips_with_torch_adam():
+    """FlatAdam.state_dict() is torch.optim.Adam's checkpoint layout (train_new_task_step2.py:380 saves it): torch's
+    Adam loads it and continues identically, and FlatAdam loads torch's."""
+    from mdil_ss_b200.parallel import FlatAdam
+    torch.manual_seed(0)
+    ws = [torch.randn(4, 3), torch.randn(5), torch.randn(2, 2, 2)]
+    pa = [torch.nn.Parameter(w.clone()) for w in ws]
+    pb = [torch.nn.Parameter(w.clone()) for w in ws]
+    fa = FlatAdam([{"params": pa[:2], "lr": 5e-6}, {"params": pa[2:]}], 5e-4)
+    ta = torch.optim.Adam([{"params": pb[:2], "lr": 5e-6}, {"params": pb[2:]}], 5e-4, (0.9, 0.999), eps=1e-8, weight_decay=1e-4)
+    gs = [[torch.randn_like(w) for w in ws] for _ in range(4)]
+
+    def run(opt, params, grads, flat):
+        opt.zero_grad()
+        for p, g in zip(params, grads):
+            if flat:
+                p.grad.copy_(g)
+            else:
+                p.grad = g.clone()
+        opt.step(allreduce=False) if flat else opt.step()
+
+    for i in range(2):
+        run(fa, pa, gs[i], True)
+        run(ta, pb, gs[i], False)
+    for a, b in zip(pa, pb):
+        assert torch.allclose(a, b, rtol=1e-6, atol=1e-7)
+    sd = fa.state_dict()
+    assert sorted(sd["state"].keys()) == [0, 1, 2] and [g["params"] for g in sd["param_groups"]] == [[0, 1], [2]]
+    assert float(sd["state"][0]["step"]) == 2.0
+    # torch's Adam continues from FlatAdam's checkpoint ...
+    pc = [torch.nn.Parameter(a.detach().clone()) for a in pa]
+    tc = torch.optim.Adam([{"params": pc[:2], "lr": 5e-6}, {"params": pc[2:]}], 5e-4, (0.9, 0.999), eps=1e-8, weight_decay=1e-4)
+    tc.load_state_dict(sd)
+    # ... and FlatAdam from torch's
+    pd = [torch.nn.Parameter(b.detach().clone()) for b in pb]
+    fd = FlatAdam([{"params": pd[:2], "lr": 5e-6}, {"params": pd[2:]}], 5e-4)
+    fd.load_state_dict(ta.state_dict())
+    for i in range(2, 4):
+        run(ta, pb, gs[i], False)
+        run(tc, pc, gs[i], False)
+        run(fd, pd, gs[i], True)
+    for b, c, d_ in zip(pb, pc, pd):
+        assert torch.allclose(b, c, rtol=1e-6, atol=1e-7) and torch.allclose(b, d_, rtol=1e-6, atol=1e-7)
+
+
+def test_transfer_previous_step_follows_the_driver():
+    """mdil_ss_b200.checkpoint.transfer_previous_step restates train_new_task_step2.py:499-529."""
+    from mdil_ss_b200.checkpoint import transfer_previous_step, add_module_prefix
+    from mdil_ss_b200.erfnet_RA_parallel import Net
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        torch.manual_seed(1)
+        old = Net([20], 1, 0)
+        torch.manual_seed(2)
+        new = Net([20, 20], 2, 1)
+    before = {k: v.clone() for k, v in new.state_dict().items()}
+    saved = add_module_prefix(old.state_dict())          # the drivers save DataParallel checkpoints
+    transfer_previous_step(saved, new, 1)
+    after = new.state_dict()
+    osd = old.state_dict()
+    for k, v in after.items():
+        if k in osd:                                                     # common tensors: taken as they are
+            assert torch.equal(v, osd[k]), k
+    for k, v in osd.items():
+        if "encoder" in k and ("parallel_conv" in k or "bn" in k) and (k.endswith(".0.weight") or k.endswith(".0.bias")):
+            k1 = k[:-len(".0.weight")] + ".1.weight" if k.endswith(".0.weight") else k[:-len(".0.bias")] + ".1.bias"
+            assert torch.equal(after[k1], v), k1                         # domain-0 adapters / BN affine -> domain 1
+        if k.startswith("decoder.0.") and "output_conv" not in k:
+            assert torch.equal(after["decoder.1." + k[len("decoder.0."):]], v)
+    for k in after:                                                      # untouched: the new head and the new domain's BN buffers
+        if k.startswith("decoder.1.output_conv") or (".1.running_" in k and "encoder" in k):
+            assert torch.equal(after[k], before[k]), k

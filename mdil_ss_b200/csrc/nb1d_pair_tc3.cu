@@ -7,7 +7,7 @@
 // What is different from nb1d_pair_tc.cu (one tile per CTA, phases in series):
 //   * one CTA per SM walks a strided list of lattice tiles (persistent); per tile the five phases
 //     load -> conv 1 (+adapter) -> epilogue 1 -> conv 2 -> epilogue 2 run on different warps and overlap:
-//       warps 0..7   epilogue warps (TMEM lane quadrant = warp & 3, interleaved 16-column sub-blocks)
+//       warps 0..7   epilogue warps (TMEM lane quadrant = warp & 3, interleaved 16-column sub-blocks, 16x256b loads)
 //       warps 8..11  loader warps: global -> registers (BN+ReLU prologue) -> hi/lo -> SWIZZLE_128B K-major operand
 //       warp 12      MMA issuer (one elected lane issues tcgen05.mma kind::tf32, M=128, N=C, K=8)
 //       warp 13      weight producer (cp.async.bulk + mbarrier ring; with a cluster, each CTA fetches 1/CL of every
@@ -16,8 +16,9 @@
 //     first 32 input channels of the tile are in shared memory, the second conv when the first 32 `mid` channels are;
 //   * the second accumulator is double-buffered in TMEM, so epilogue 2 of tile i overlaps the MMAs of tile i+1;
 //     for C = 64 the activation operand is double-buffered too (loads run one tile ahead);
-//   * epilogue inputs (ReLU masks, p, dy, y) are prefetched with coalesced loads before the accumulator is waited
-//     for; per-channel BatchNorm sums are reduced with a register butterfly and kept per warp across all tiles.
+//   * the epilogues read TMEM with the 16x256b shape (four lanes own 32 contiguous bytes of a pixel row): their inputs
+//     (ReLU masks, p, dy, y; prefetched before the accumulator is waited for) and results use sector-filling 8-byte
+//     global accesses without shared-memory staging; per-channel BatchNorm sums: warp shuffles -> shared -> fp64 atomics.
 #include "kernels.cuh"
 
 #include <stdio.h>
@@ -108,18 +109,6 @@ __device__ __forceinline__ void mma_tf32_w(uint32_t tmem_d, uint32_t a_lo, uint3
       "setp.ne.b32 p, %6, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}" ::"r"(tmem_d), "r"(a_lo),
       "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc) : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
 // 16 TMEM lanes x 16 columns: lane l gets rows (l>>2), (l>>2)+8 and columns 2(l&3), +1 of each 8-column group:
 // v[4c + 2k + e] = (row (l>>2) + 8k, column 8c + 2(l&3) + e).  No wait: several loads may be in flight.
 __device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, float (&v)[8]) {
@@ -131,25 +120,7 @@ __device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, float (&v)[8]
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// sum of two 16-column accumulator pieces (both loads in flight, one wait)
-__device__ __forceinline__ void tmem_ld16x2(uint32_t ta, uint32_t tb, float (&v)[16]) {
-  uint32_t r[16], q[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(ta));
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]), "=r"(q[8]),
-        "=r"(q[9]), "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15])
-      : "r"(tb));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + __uint_as_float(q[i]);
-}
+// weights are split once per step at pack time with the hardware rounding
 __device__ __forceinline__ float tf32_rna(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -178,45 +149,6 @@ __device__ __forceinline__ void cluster_sync_all() {
 
 // byte offset of (row, 16-byte chunk c) inside a SWIZZLE_128B slab (slab bases are 1024-byte aligned)
 __device__ __forceinline__ uint32_t sw128_off(int row, int c) { return (uint32_t)row * 128 + ((uint32_t)(c ^ (row & 7)) << 4); }
-// staging tile [32 rows][16 floats]: 16-byte chunk c of row r lives at chunk c ^ ((r >> 1) & 3)  (conflict-free for both
-// the row-per-lane view and the coalesced 4-lanes-per-row view)
-__device__ __forceinline__ float4* stg_ptr(float* stg, int r, int c) {
-  return reinterpret_cast<float4*>(stg + r * 16 + ((c ^ ((r >> 1) & 3)) << 2));
-}
-
-// sum over the 32 lanes of 16 per-lane values: returns, in every lane, the total of value index
-// ((lane>>4)&1)*8 + ((lane>>3)&1)*4 + ((lane>>2)&1)*2 + ((lane>>1)&1)   (16 shuffles instead of 80)
-__device__ __forceinline__ float butterfly16(float (&v)[16], int lane) {
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const bool up = (lane & 16) != 0;
-    const float send = up ? v[i] : v[i + 8];
-    const float recv = __shfl_xor_sync(0xffffffffu, send, 16);
-    v[i] = (up ? v[i + 8] : v[i]) + recv;
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const bool up = (lane & 8) != 0;
-    const float send = up ? v[i] : v[i + 4];
-    const float recv = __shfl_xor_sync(0xffffffffu, send, 8);
-    v[i] = (up ? v[i + 4] : v[i]) + recv;
-  }
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const bool up = (lane & 4) != 0;
-    const float send = up ? v[i] : v[i + 2];
-    const float recv = __shfl_xor_sync(0xffffffffu, send, 4);
-    v[i] = (up ? v[i + 2] : v[i]) + recv;
-  }
-  {
-    const bool up = (lane & 2) != 0;
-    const float send = up ? v[0] : v[1];
-    const float recv = __shfl_xor_sync(0xffffffffu, send, 2);
-    v[0] = (up ? v[1] : v[0]) + recv;
-  }
-  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
-}
-
 struct TileCoord { int n, cb, ul0, vl0; bool dummy; };
 
 template <int C>

@@ -33,7 +33,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="step1", choices=["step1", "step2", "step3"])
+    ap.add_argument("--workload", default="step1", choices=["step1", "step2", "step3", "multitask"])
+    ap.add_argument("--full-res", action="store_true", help="1024x2048 crops (BASELINE config 5) instead of 512x1024")
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="crops per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ncu-step", action="store_true",
@@ -49,6 +50,9 @@ def workload_name(args):
     if args.workload == "step2":
         return (f"Step-2 CS->BDD train (student fwd x2 + teacher fwd, CE2d + 0.1*KD, bwd, allreduce, Adam), 20/20 cls, "
                 f"batch {args.batch}/GPU, {H}x{W} synthetic")
+    if args.workload == "multitask":
+        return (f"Multi-task joint CS+BDD+IDD over the RAP network (one visit per dataset and step: fwd, CE2d, bwd, "
+                f"allreduce, Adam), 20/20/27 cls, batch {args.batch}/GPU and dataset, {H}x{W} synthetic")
     return (f"Step-3 CS|BDD->IDD train (CE step, then student fwd x2 + teacher fwd x2 + 0.1*(KD+KD) step: two "
             f"all-reduce + Adam per iteration), 20/20/27 cls, batch {args.batch}/GPU, {H}x{W} synthetic")
 
@@ -104,9 +108,10 @@ def oracle_step_factory(workload, n):
     from oracle import erfnet_rap_oracle as oracle
     g = torch.Generator().manual_seed(1234)
     images = torch.rand(n, 3, H, W, generator=g)
-    labels = torch.randint(0, 27 if workload == "step3" else NCLS, (n, 1, H // 32, W // 32),
+    labels = torch.randint(0, 27 if workload in ("step3", "multitask") else NCLS, (n, 1, H // 32, W // 32),
                            generator=g).repeat_interleave(32, 2).repeat_interleave(32, 3)
-    weight = torch.tensor({"step1": oracle.WEIGHT_CITY, "step2": oracle.WEIGHT_BDD, "step3": oracle.WEIGHT_IDD}[workload])
+    weight = torch.tensor({"step1": oracle.WEIGHT_CITY, "step2": oracle.WEIGHT_BDD, "step3": oracle.WEIGHT_IDD,
+                           "multitask": oracle.WEIGHT_IDD}[workload])
     if workload == "step1":
         sd = oracle.init_state_dict([NCLS], 1, seed=0)
         state = [dict() for _ in oracle.param_names(sd)]
@@ -116,6 +121,17 @@ def oracle_step_factory(workload, n):
             noise = oracle.make_dropout_noise(n, True)
             loss, _, _ = oracle.step1_iteration(sd, images, labels, weight, 0, noise, state)
             return float(loss)
+    elif workload == "multitask":
+        sd = oracle.init_state_dict([NCLS, NCLS, 27], 3, seed=0)
+        state = {}
+        ws = [torch.tensor(w) for w in (oracle.WEIGHT_CITY, oracle.WEIGHT_BDD, oracle.WEIGHT_IDD)]
+        lab20 = labels.clamp(max=NCLS - 1)
+
+        def step():
+            torch.manual_seed(7)
+            noises = [oracle.make_dropout_noise(n, True) for _ in range(3)]
+            losses = oracle.multitask_iteration(sd, [(images, lab20), (images, lab20), (images, labels)], ws, noises, state)
+            return float(losses[-1])
     elif workload == "step3":
         sd_old = oracle.init_state_dict([NCLS, NCLS], 2, seed=0)
         sd = oracle.init_state_dict([NCLS, NCLS, 27], 3, seed=1)
@@ -210,16 +226,21 @@ def run_ours(args):
         elif args.workload == "step2":
             model_old = Net([NCLS], 1, 0).to(dev)
             model = Net([NCLS, NCLS], 2, 1).to(dev)
+        elif args.workload == "multitask":
+            model = Net([NCLS, NCLS, 27], 3, 0).to(dev)
         else:
             model_old = Net([NCLS, NCLS], 2, 1).to(dev)
             model = Net([NCLS, NCLS, 27], 3, 2).to(dev)
     broadcast_module(model)
-    ncls_labels = NCLS
+    ncls_labels = 27 if args.workload == "multitask" else NCLS
     if args.workload == "step1":
         trainer = Step1Trainer(model, class_weights("cityscapes", dev))
     elif args.workload == "step2":
         broadcast_module(model_old)
         trainer = Step2Trainer(model, model_old, class_weights("BDD", dev), 1, 0.1)
+    elif args.workload == "multitask":
+        from mdil_ss_b200.train_step import MultiTaskTrainer
+        trainer = MultiTaskTrainer(model, [class_weights(d_, dev) for d_ in ("cityscapes", "BDD", "IDD")])
     else:
         from mdil_ss_b200.train_step import Step3Trainer
         broadcast_module(model_old)
@@ -232,6 +253,12 @@ def run_ours(args):
                 .repeat_interleave(32, 2).repeat_interleave(32, 3).contiguous().pin_memory())
     images = images_h.to(dev, non_blocking=True)
     labels = labels_h.to(dev, non_blocking=True)
+
+    crops_per_step = n
+    if args.workload == "multitask":      # three dataset visits per step (labels of the 20-class sets clipped to their range)
+        crops_per_step = 3 * n
+        _orig_step = trainer.step
+        trainer.step = lambda x, y: _orig_step([(x, y.clamp(max=NCLS - 1)), (x, y.clamp(max=NCLS - 1)), (x, y)])[-1]
 
     def step_resident():
         return trainer.step(images, labels)
@@ -289,13 +316,13 @@ def run_ours(args):
     lib.mdil_profile_end(tot, cnt, nk)
     launches = _lib.launches() - launches0
     clocks = sampler.stop() if rank == 0 else None
-    value = world * n * args.steps / (ms_total / 1e3)
+    value = world * crops_per_step * args.steps / (ms_total / 1e3)
 
     # ---- end-to-end: host buffers, H2D of the inputs and D2H of the loss inside the timed region
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
-    e2e_value = world * n * args.steps / (ms_e2e / 1e3)
+    e2e_value = world * crops_per_step * args.steps / (ms_e2e / 1e3)
 
     if rank == 0:
         peaks = {}
@@ -353,7 +380,11 @@ def run_ours(args):
 
 
 def main():
+    global H, W, METRIC
     args = parse()
+    if args.full_res:
+        H, W = 1024, 2048
+        METRIC = "train_crops_per_sec_1024x2048"
     if args.impl == "reference":
         run_reference(args)
     else:

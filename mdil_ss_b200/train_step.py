@@ -150,3 +150,31 @@ class Step3Trainer:
         kd_loss.backward()
         self.optimizer.step()
         return ce_loss.detach(), kd_loss.detach()
+
+
+class MultiTaskTrainer:
+    """train_multi_task.py:209-265 run over the RAP network (BASELINE config 5): every iteration visits the
+    datasets in turn -- forward on domain i, its class-weighted CE, backward, one optimiser step -- with the encoder
+    at lr 5e-4 / nb_tasks and the decoders at 5e-4 (:209-218).  Tensors a visit does not reach (the other domains'
+    adapters, BatchNorms and decoders) are left untouched by that visit's optimiser step, as torch.optim.Adam does."""
+
+    def __init__(self, model, weights: Sequence[torch.Tensor], lr: float = 5e-4):
+        self.model = model
+        self.nb_tasks = len(weights)
+        self.criteria = [CrossEntropyLoss2d(w, global_norm=True).to(w.device) for w in weights]
+        params = list(model.named_parameters())
+        self.optimizer = FlatAdam([{"params": [p for n, p in params if "encoder" in n], "lr": lr / self.nb_tasks},
+                                   {"params": [p for n, p in params if "decoder" in n]}], lr)
+
+    def step(self, batches):
+        """``batches[i] = (images_i, labels_i)`` for dataset i; returns the list of CE losses."""
+        self.model.train()
+        losses = []
+        for ind, (images, labels) in enumerate(batches):
+            outputs = self.model(images, ind)
+            self.optimizer.zero_grad()
+            loss = self.criteria[ind](outputs, labels[:, 0])
+            loss.backward()
+            self.optimizer.step()
+            losses.append(loss.detach())
+        return losses

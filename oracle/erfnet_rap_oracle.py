@@ -345,6 +345,31 @@ def step3_iteration(sd: SD, sd_old: SD, images: torch.Tensor, labels: torch.Tens
     return ce.detach(), kd.detach(), out_t.detach(), g_ce, g_kd
 
 
+def multitask_iteration(sd: SD, batches, weights, noises=None, opt_state: Optional[dict] = None, lr: float = 5e-4):
+    """One iteration of train_multi_task.py:244-265 over the RAP network: for every dataset i in turn, fwd(task i) ->
+    CE_i -> backward -> Adam step (encoder tensors at lr / nb_tasks, decoder tensors at lr, :209-218); tensors without a
+    gradient in a visit are skipped by that visit's step.  Returns the list of losses."""
+    nb = len(batches)
+    names = param_names(sd)
+    state = opt_state if opt_state is not None else {}
+    for n in names:
+        state.setdefault(n, {})
+    losses = []
+    for ind, (images, labels) in enumerate(batches):
+        work = _with_grad(sd, names)
+        logits = net_forward(work, images, ind, True, None if noises is None else noises[ind])
+        loss = cross_entropy2d(logits, labels[:, 0], weights[ind])
+        grads = torch.autograd.grad(loss, [work[n] for n in names], allow_unused=True)
+        got = {n: g for n, g in zip(names, grads) if g is not None}
+        with torch.no_grad():
+            enc = [n for n in names if "encoder" in n and n in got]
+            dec = [n for n in names if "decoder" in n and n in got]
+            adam_step([sd[n] for n in enc], [got[n] for n in enc], [state[n] for n in enc], lr / nb)
+            adam_step([sd[n] for n in dec], [got[n] for n in dec], [state[n] for n in dec], lr)
+        losses.append(loss.detach())
+    return losses
+
+
 # ------------------------------------------------------- constructor restatement
 def init_state_dict(num_classes: Sequence[int] = (20,), nb_tasks: int = 1, seed: Optional[int] = None) -> SD:
     """Restates Net.__init__ (models/erfnet_RA_parallel.py:195-205 and the block constructors :14-19, :68-88,

@@ -254,6 +254,68 @@ def test_step3_iteration_matches_reference():
         assert abs(d - ref_delta) <= 6e-2 * ref_delta + 1e-6, f"{k}: |delta| {d} vs reference {ref_delta}"
 
 
+def test_multitask_iteration_matches_oracle():
+    """MultiTaskTrainer (train_multi_task.py:244-265 over the RAP network): one round over three datasets vs the oracle's
+    restatement -- losses, and which tensors each visit's optimiser step moves."""
+    from mdil_ss_b200.train_step import MultiTaskTrainer
+    classes = [20, 20, 27]
+    sd0 = make_sd(classes, 30, 31)
+    sd_ref = oracle.clone_sd(sd0)
+    net = _net(classes, sd0)
+    gen = torch.Generator().manual_seed(600)
+    batches = [(torch.rand(2, 3, 32, 64, generator=gen), torch.randint(0, c, (2, 1, 32, 64), generator=gen)) for c in classes]
+    weights = [torch.tensor(w) for w in (oracle.WEIGHT_CITY, oracle.WEIGHT_BDD, oracle.WEIGHT_IDD)]
+    torch.manual_seed(77)
+    noises = [oracle.make_dropout_noise(2, True) for _ in classes]
+    ref_losses = oracle.multitask_iteration(sd_ref, batches, weights, noises)
+    tr = MultiTaskTrainer(net, [w.to(DEV) for w in weights])
+    streams = [_to_dev(nz) for nz in noises]
+    orig = net.forward
+    calls = []
+
+    def fwd(inp, task, drop_noise=None):
+        calls.append(task)
+        return orig(inp, task, drop_noise=streams[len(calls) - 1])
+
+    net.forward = fwd
+    losses = tr.step([(x.to(DEV), y.to(DEV)) for x, y in batches])
+    assert calls == [0, 1, 2]
+    for a, b in zip(losses, ref_losses):
+        assert abs(float(a) - float(b)) <= TOL * abs(float(b))
+    after = net.state_dict()
+    for k in oracle.param_names(sd_ref):
+        ref_delta = float((sd_ref[k].double() - sd0[k].double()).abs().sum())
+        d = float((after[k].double().cpu() - sd0[k].double()).abs().sum())
+        if ref_delta == 0.0:
+            assert d == 0.0, f"{k} must not move"
+        elif ref_delta > 1e-3 * sd0[k].numel() * 5e-4:      # skip tensors whose gradient is mathematically zero (Adam noise)
+            assert abs(d - ref_delta) <= 8e-2 * ref_delta + 1e-6, f"{k}: |delta| {d} vs oracle {ref_delta}"
+
+
+def test_max_size_1024x2048_forward_backward():
+    """BASELINE config 5 resolution (1024 x 2048): shape contract, finite outputs and gradients, and in eval mode a crop's
+    logits do not depend on its batch neighbour (bit-exact)."""
+    from mdil_ss_b200.losses import CrossEntropyLoss2d
+    torch.manual_seed(0)
+    net = _net([20, 20, 27], make_sd([20, 20, 27], 3, 4))
+    x = torch.rand(2, 3, 1024, 2048, device=DEV)
+    net.eval()
+    with torch.no_grad():
+        y = net(x, 2)
+        y0 = net(x[:1].contiguous(), 2)
+    assert tuple(y.shape) == (2, 27, 1024, 2048) and torch.isfinite(y).all()
+    assert torch.equal(y[:1], y0)
+    del y, y0
+    net.train()
+    labels = torch.randint(0, 27, (2, 32, 64), device=DEV).repeat_interleave(32, 1).repeat_interleave(32, 2)
+    loss = CrossEntropyLoss2d(torch.tensor(oracle.WEIGHT_IDD, device=DEV))(net(x, 2), labels)
+    loss.backward()
+    assert np.isfinite(float(loss))
+    g = net.encoder.layers[8].conv3x1_2.weight.grad
+    assert g is not None and torch.isfinite(g).all() and float(g.abs().sum()) > 0
+    assert net.decoder[0].output_conv.weight.grad is None          # other domains' heads are not reached
+
+
 def test_device_prefetcher_round_trip():
     """mdil_ss_b200.data.DevicePrefetcher: the batch handed back is the batch that was put (copied on a side stream)."""
     from mdil_ss_b200.data import DevicePrefetcher

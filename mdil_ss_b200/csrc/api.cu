@@ -155,7 +155,7 @@ size_t mdil_nb1d_fwd_workspace_bytes(const mdil_nb1d_desc* d) { return 256 + (si
 size_t mdil_nb1d_bwd_workspace_bytes(const mdil_nb1d_desc* d) {
   size_t T = align_up((size_t)d->N * d->H * d->W * d->C * sizeof(float), 256);
   return 3 * T + (size_t)4 * d->C * sizeof(double) + (size_t)6 * d->C * sizeof(float) +
-         (size_t)3 * d->C * d->C * sizeof(float) + 10 * 256;
+         ((size_t)18 * d->C * d->C + 6 * d->C) * sizeof(float) + 10 * 256;   // 6 accumulators [3][C][C] + 6 bias sums [C]
 }
 
 int mdil_nb1d_pack(const mdil_nb1d_desc* d, const mdil_nb1d_weights* w, float* packed, void* stream) {
@@ -216,23 +216,27 @@ int mdil_nb1d_fwd(const mdil_nb1d_desc* d, const float* x, const mdil_nb1d_weigh
 
 // One weight gradient of the block: tensor-core path (C = 64, 128) or the generic FFMA tap kernel.
 // taps: 3 (vertical when vert != 0, else horizontal, dilation d) or 1 (1x1 adapter).
+// (tensor-core path: `acc_scratch` = this gradient's own zeroed [taps][C][C] slot; its unpack is deferred to `ul`)
 static int nb1d_wgrad(const mdil_nb1d_desc* d, int dil, bool vert, int taps, const float* A, const float* sc,
-                      const float* sh, const float* G, float* dW, float* db, float* acc_scratch, cudaStream_t s) {
+                      const float* sh, const float* G, float* dW, float* db, float* acc_scratch, float* db_scratch,
+                      UnpackList* ul, cudaStream_t s) {
   const int C = d->C;
   if (dW == nullptr) {
     MDIL_REQUIRE(db == nullptr, "nb1d_bwd: bias gradient without weight gradient is not supported");
     return 0;
   }
-  if (db != nullptr) MDIL_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * C, s));
   const long s_ci = taps, s_co = (long)C * taps, s_t = taps == 1 ? 0 : 1;   // torch layout [co][ci][taps]
+  if (!use_tc_wgrad(C) && db != nullptr) MDIL_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * C, s));
   if (use_tc_wgrad(C)) {
-    MDIL_CUDA(cudaMemsetAsync(acc_scratch, 0, sizeof(float) * (size_t)C * C * taps, s));
     WgradTcArgs w;
     memset(&w, 0, sizeof(w));
-    w.A = A; w.a_scale = sc; w.a_shift = sh; w.G = G; w.dWacc = acc_scratch; w.db = db;
+    w.A = A; w.a_scale = sc; w.a_shift = sh; w.G = G; w.dWacc = acc_scratch; w.db = db != nullptr ? db_scratch : nullptr;
     w.N = d->N; w.H = d->H; w.W = d->W; w.C = C; w.dil = dil; w.ntaps = taps; w.vert = vert ? 1 : 0;
     MDIL_TRY(launch_wgrad_tc(w, s));
-    return launch_wgrad_unpack(acc_scratch, dW, C, taps, s_ci, s_co, s_t, s);
+    UnpackItem& it = ul->item[ul->n++];
+    it.acc = acc_scratch; it.dW = dW; it.ntaps = taps; it.s_ci = s_ci; it.s_co = s_co; it.s_t = s_t;
+    it.dbacc = db_scratch; it.db = db;
+    return 0;
   }
   MDIL_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)C * C * taps, s));
   ConvGeom g = taps == 1 ? pointwise_geom(d->N, d->H, d->W, C) : taps3_geom(d->N, d->H, d->W, C, dil, vert);
@@ -261,7 +265,12 @@ int mdil_nb1d_bwd(const mdil_nb1d_desc* d, const float* dy, const float* x, cons
   float* T1 = cv.take<float>(T);
   float* T2 = cv.take<float>(T);
   float* T3 = cv.take<float>(T);
-  float* wacc = cv.take<float>((size_t)3 * C * C);   // tensor-core weight-gradient accumulator [3][C][C]
+  float* wacc = cv.take<float>((size_t)18 * C * C + 6 * C);  // six accumulators [3][C][C], then six bias sums [C]
+  const size_t WS = (size_t)3 * C * C;
+  float* bacc = wacc + 6 * WS;
+  UnpackList ul;
+  ul.n = 0;
+  if (use_tc_wgrad(C)) MDIL_CUDA(cudaMemsetAsync(wacc, 0, sizeof(float) * (18 * (size_t)C * C + 6 * C), s));
   const float* st1 = sv->stats;
   const float* st2 = sv->stats + 4 * C;
   MDIL_CUDA(cudaMemsetAsync(sums2, 0, 2 * C * sizeof(double), s));
@@ -285,10 +294,10 @@ int mdil_nb1d_bwd(const mdil_nb1d_desc* d, const float* dy, const float* x, cons
   if (stop == 2) return 0;
 
   // ---- weight gradients of pair 2
-  MDIL_TRY(nb1d_wgrad(d, d->dil, false, 3, sv->c, nullptr, nullptr, T1, gr->w13_2, gr->b13_2, wacc, s));
+  MDIL_TRY(nb1d_wgrad(d, d->dil, false, 3, sv->c, nullptr, nullptr, T1, gr->w13_2, gr->b13_2, wacc + 0 * WS, bacc + 0 * C, &ul, s));
   if (d->has_adapter)
-    MDIL_TRY(nb1d_wgrad(d, 1, true, 1, sv->p, st1 + 2 * C, st1 + 3 * C, T1, gr->wp2, gr->bp2, wacc, s));
-  MDIL_TRY(nb1d_wgrad(d, d->dil, true, 3, sv->p, st1 + 2 * C, st1 + 3 * C, T2, gr->w31_2, gr->b31_2, wacc, s));
+    MDIL_TRY(nb1d_wgrad(d, 1, true, 1, sv->p, st1 + 2 * C, st1 + 3 * C, T1, gr->wp2, gr->bp2, wacc + 1 * WS, bacc + 1 * C, &ul, s));
+  MDIL_TRY(nb1d_wgrad(d, d->dil, true, 3, sv->p, st1 + 2 * C, st1 + 3 * C, T2, gr->w31_2, gr->b31_2, wacc + 2 * WS, bacc + 2 * C, &ul, s));
 
   if (stop == 3) return 0;
   // ---- BN1 backward: dq -> dp (overwrites ds)
@@ -301,10 +310,10 @@ int mdil_nb1d_bwd(const mdil_nb1d_desc* d, const float* dy, const float* x, cons
   MDIL_TRY(launch_pair(a, s));
 
   // ---- weight gradients of pair 1
-  MDIL_TRY(nb1d_wgrad(d, 1, false, 3, sv->a, nullptr, nullptr, T1, gr->w13_1, gr->b13_1, wacc, s));
-  if (d->has_adapter) MDIL_TRY(nb1d_wgrad(d, 1, true, 1, x, nullptr, nullptr, T1, gr->wp1, gr->bp1, wacc, s));
-  MDIL_TRY(nb1d_wgrad(d, 1, true, 3, x, nullptr, nullptr, T2, gr->w31_1, gr->b31_1, wacc, s));
-  return 0;
+  MDIL_TRY(nb1d_wgrad(d, 1, false, 3, sv->a, nullptr, nullptr, T1, gr->w13_1, gr->b13_1, wacc + 3 * WS, bacc + 3 * C, &ul, s));
+  if (d->has_adapter) MDIL_TRY(nb1d_wgrad(d, 1, true, 1, x, nullptr, nullptr, T1, gr->wp1, gr->bp1, wacc + 4 * WS, bacc + 4 * C, &ul, s));
+  MDIL_TRY(nb1d_wgrad(d, 1, true, 3, x, nullptr, nullptr, T2, gr->w31_1, gr->b31_1, wacc + 5 * WS, bacc + 5 * C, &ul, s));
+  return launch_wgrad_unpack_multi(ul, C, s);
 }
 
 // =============================================================================== downsampler

@@ -130,6 +130,9 @@ struct WgradTcArgs {
 };
 int launch_wgrad_tc(const WgradTcArgs& a, cudaStream_t s);
 int launch_wgrad_unpack(const float* acc, float* dW, int C, int ntaps, long s_ci, long s_co, long s_t, cudaStream_t s);
+struct UnpackItem { const float* acc; float* dW; int ntaps; long s_ci, s_co, s_t; const float* dbacc; float* db; };
+struct UnpackList { int n; UnpackItem item[6]; };
+int launch_wgrad_unpack_multi(const UnpackList& ul, int C, cudaStream_t s);   // one launch for a block's weight gradients
 
 // ---------------------------------------------------------------- head_loss.cu
 int launch_outconv_fwd(const float* x, const float* w, const float* bias, float* logits, int N, int H, int W, int Ccls,

@@ -412,6 +412,20 @@ __global__ void wgrad_unpack_kernel(const float* __restrict__ acc, float* __rest
   }
 }
 
+// all (up to 6) tensor-core weight gradients of a block leave their [ntaps][ci][co] accumulators in one launch
+__global__ void wgrad_unpack_multi_kernel(const UnpackList ul, int C) {
+  const UnpackItem& it = ul.item[blockIdx.y];
+  const long total = (long)it.ntaps * C * C;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % C);
+    const int ci = (int)((i / C) % C);
+    const int t = (int)(i / ((long)C * C));
+    it.dW[ci * it.s_ci + co * it.s_co + t * it.s_t] = it.acc[i];
+  }
+  if (it.db != nullptr && blockIdx.x == 0)
+    for (int c = threadIdx.x; c < C; c += blockDim.x) it.db[c] = it.dbacc[c];
+}
+
 template <int C>
 int launch_c(const WgradTcArgs& a, cudaStream_t s) {
   using K = Cfg<C>;
@@ -461,6 +475,16 @@ int launch_wgrad_tc(const WgradTcArgs& a_in, cudaStream_t s) {
     case 64: return wtc::launch_c<64>(a, s);
     default: return set_error(-2, "wgrad_tc: C must be 64 or 128", __FILE__, __LINE__);
   }
+}
+
+int launch_wgrad_unpack_multi(const UnpackList& ul, int C, cudaStream_t s) {
+  if (ul.n == 0) return 0;
+  const long total = 3L * C * C;
+  int grid = (int)((total + 255) / 256);
+  if (grid > kNumSMs) grid = kNumSMs;
+  wtc::wgrad_unpack_multi_kernel<<<dim3((unsigned)grid, (unsigned)ul.n), 256, 0, s>>>(ul, C);
+  MDIL_LAUNCH_CHECK();
+  return 0;
 }
 
 int launch_wgrad_unpack(const float* acc, float* dW, int C, int ntaps, long s_ci, long s_co, long s_t, cudaStream_t s) {

@@ -185,14 +185,11 @@ int mdil_nb1d_fwd(const mdil_nb1d_desc* d, const float* x, const mdil_nb1d_weigh
   const double count = (double)d->N * (double)HW;
   cudaStream_t s = S(stream);
   Carver cv(ws);
-  double* sums1 = cv.take<double>(2 * C);
-  double* sums2 = cv.take<double>(2 * C);
+  double* sums1 = cv.take<double>(4 * C);     // [2][2][C]: both pairs' sums, one memset
+  double* sums2 = sums1 + 2 * C;
   float* st1 = sv->stats;
   float* st2 = sv->stats + 4 * C;
-  if (d->train) {
-    MDIL_CUDA(cudaMemsetAsync(sums1, 0, 2 * C * sizeof(double), s));
-    MDIL_CUDA(cudaMemsetAsync(sums2, 0, 2 * C * sizeof(double), s));
-  }
+  if (d->train) MDIL_CUDA(cudaMemsetAsync(sums1, 0, 4 * C * sizeof(double), s));
   PairArgs a;
   memset(&a, 0, sizeof(a));
   a.N = d->N; a.H = d->H; a.W = d->W; a.C = C; a.has_adapter = d->has_adapter; a.vert_first = 1; a.epi = kEpiFwd;
@@ -258,8 +255,8 @@ int mdil_nb1d_bwd(const mdil_nb1d_desc* d, const float* dy, const float* x, cons
   const double count = (double)N * (double)HW;
   cudaStream_t s = S(stream);
   Carver cv(ws);
-  double* sums2 = cv.take<double>(2 * C);
-  double* sums1 = cv.take<double>(2 * C);
+  double* sums2 = cv.take<double>(4 * C);     // [2][2][C]: both BatchNorms' backward sums, one memset
+  double* sums1 = sums2 + 2 * C;
   float* coef2 = cv.take<float>(3 * C);
   float* coef1 = cv.take<float>(3 * C);
   float* T1 = cv.take<float>(T);
@@ -273,8 +270,7 @@ int mdil_nb1d_bwd(const mdil_nb1d_desc* d, const float* dy, const float* x, cons
   if (use_tc_wgrad(C)) MDIL_CUDA(cudaMemsetAsync(wacc, 0, sizeof(float) * (18 * (size_t)C * C + 6 * C), s));
   const float* st1 = sv->stats;
   const float* st2 = sv->stats + 4 * C;
-  MDIL_CUDA(cudaMemsetAsync(sums2, 0, 2 * C * sizeof(double), s));
-  MDIL_CUDA(cudaMemsetAsync(sums1, 0, 2 * C * sizeof(double), s));
+  MDIL_CUDA(cudaMemsetAsync(sums2, 0, 4 * C * sizeof(double), s));
 
   // ---- BN2 backward (+ ReLU mask of y, dropout): ds
   MDIL_TRY(launch_bn_bwd_stats(dy, y, drop_mask, sv->s, st2, sums2, N, HW, C, s));

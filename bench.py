@@ -362,7 +362,7 @@ def run_ours(args):
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": workload_name(args), "global_batch": world * n, "crop": f"{H}x{W}",
                            "parallelism": f"dp{world}", "l2": "per-step activations (>2 GB) exceed the 126 MB L2",
-                           "collective": "one NCCL all-reduce of the flat fp32 gradient buffer per optimiser step"},
+                           "collective": "one NCCL all-reduce of the flat fp32 gradient buffer per optimiser step (+ a 16-byte all-reduce of the CE accumulators: DataParallel's global loss normalisation)"},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                         "h2d_bytes_per_step": images_h.numel() * 4 + labels_h.numel() * 8, "d2h_bytes_per_step": 4},

@@ -181,3 +181,28 @@ def test_transfer_previous_step_follows_the_driver():
     for k in after:                                                      # untouched: the new head and the new domain's BN buffers
         if k.startswith("decoder.1.output_conv") or (".1.running_" in k and "encoder" in k):
             assert torch.equal(after[k], before[k]), k
+
+
+def test_imagenet_encoder_rename():
+    from mdil_ss_b200.checkpoint import imagenet_encoder_rename, strip_module_prefix
+    sd = {"module.features.encoder.initial_block.conv.weight": torch.zeros(1), "module.extralayers.w": torch.ones(1)}
+    out = imagenet_encoder_rename(sd)
+    assert set(out) == {"module.encoder.initial_block.conv.weight", "module.extralayers.w"}
+    assert set(strip_module_prefix(out)) == {"encoder.initial_block.conv.weight", "extralayers.w"}
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the reference algorithm on the host cores) needs no GPU and prints one JSON line
+    with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(repo, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600, cwd=repo)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "train_crops_per_sec_512x1024" and line["unit"] == "crops/s"
+    assert line["higher_is_better"] is True and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0

@@ -276,8 +276,7 @@ int mdil_nb1d_bwd(const mdil_nb1d_desc* d, const float* dy, const float* x, cons
   MDIL_TRY(launch_bn_bwd_stats(dy, y, drop_mask, sv->s, st2, sums2, N, HW, C, s));
   MDIL_TRY(launch_bn_bwd_finalize(sums2, count, C, w->bn2.weight, st2, coef2, gr->bn2_w, gr->bn2_b, s));
   MDIL_TRY(launch_bn_bwd_apply(dy, y, drop_mask, sv->s, st2, coef2, T1, N, HW, C, s));
-  const char* dbg = getenv("MDIL_DEBUG_STOP");
-  const int stop = dbg ? atoi(dbg) : 0;
+  static const int stop = [] { const char* dbg = getenv("MDIL_DEBUG_STOP"); return dbg ? atoi(dbg) : 0; }();   // tools/debug_nb1d.py
   if (stop == 1) return 0;
 
   // ---- pair 2 backward: ds -> dc' -> dq (masked by r>0), sums for BN1 backward

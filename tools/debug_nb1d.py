@@ -56,7 +56,7 @@ def run(C, dil, rap, N, H, W, pdrop):
         nonlocal base
         base = (base + 255) // 256 * 256
         o = base; base += nbytes; return o
-    take(2 * C * 8); take(2 * C * 8); take(3 * C * 4); take(3 * C * 4)
+    take(4 * C * 8); take(3 * C * 4); take(3 * C * 4)     # sums [2][2][C] fp64, coef2, coef1 (api.cu: mdil_nb1d_bwd)
     o1 = take(Tb); o2 = take(Tb); o3 = take(Tb)
     view = lambda o: ws[o:o + Tb].view(torch.float32).view(N, H, W, C).permute(0, 3, 1, 2)
     # dp = grad wrt p ; da' = grad wrt (pre-relu a)*mask = a.grad * (a>0) ; dq = q.grad

@@ -166,15 +166,16 @@ class MultiTaskTrainer:
         self.optimizer = FlatAdam([{"params": [p for n, p in params if "encoder" in n], "lr": lr / self.nb_tasks},
                                    {"params": [p for n, p in params if "decoder" in n]}], lr)
 
+    def visit(self, ind: int, images, labels):
+        """One dataset visit (train_multi_task.py:247-262): forward on domain ``ind``, CE, backward, optimiser step."""
+        self.model.train()
+        outputs = self.model(images, ind)
+        self.optimizer.zero_grad()
+        loss = self.criteria[ind](outputs, labels[:, 0])
+        loss.backward()
+        self.optimizer.step()
+        return loss.detach()
+
     def step(self, batches):
         """``batches[i] = (images_i, labels_i)`` for dataset i; returns the list of CE losses."""
-        self.model.train()
-        losses = []
-        for ind, (images, labels) in enumerate(batches):
-            outputs = self.model(images, ind)
-            self.optimizer.zero_grad()
-            loss = self.criteria[ind](outputs, labels[:, 0])
-            loss.backward()
-            self.optimizer.step()
-            losses.append(loss.detach())
-        return losses
+        return [self.visit(ind, images, labels) for ind, (images, labels) in enumerate(batches)]

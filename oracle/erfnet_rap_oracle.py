@@ -345,10 +345,12 @@ def step3_iteration(sd: SD, sd_old: SD, images: torch.Tensor, labels: torch.Tens
     return ce.detach(), kd.detach(), out_t.detach(), g_ce, g_kd
 
 
-def multitask_iteration(sd: SD, batches, weights, noises=None, opt_state: Optional[dict] = None, lr: float = 5e-4):
+def multitask_iteration(sd: SD, batches, weights, noises=None, opt_state: Optional[dict] = None, lr: float = 5e-4,
+                        only: Optional[Sequence[int]] = None):
     """One iteration of train_multi_task.py:244-265 over the RAP network: for every dataset i in turn, fwd(task i) ->
     CE_i -> backward -> Adam step (encoder tensors at lr / nb_tasks, decoder tensors at lr, :209-218); tensors without a
-    gradient in a visit are skipped by that visit's step.  Returns the list of losses."""
+    gradient in a visit are skipped by that visit's step.  Returns the list of losses.  ``only`` restricts the call to
+    those dataset visits (the optimiser state carries over through ``opt_state``), so a test can compare visit by visit."""
     nb = len(batches)
     names = param_names(sd)
     state = opt_state if opt_state is not None else {}
@@ -356,6 +358,8 @@ def multitask_iteration(sd: SD, batches, weights, noises=None, opt_state: Option
         state.setdefault(n, {})
     losses = []
     for ind, (images, labels) in enumerate(batches):
+        if only is not None and ind not in only:
+            continue
         work = _with_grad(sd, names)
         logits = net_forward(work, images, ind, True, None if noises is None else noises[ind])
         loss = cross_entropy2d(logits, labels[:, 0], weights[ind])

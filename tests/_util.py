@@ -1,4 +1,5 @@
 """Shared helpers of the test-suite (test infrastructure: may import oracle/)."""
+import contextlib
 import os
 import sys
 
@@ -31,6 +32,29 @@ def noise_list(npz, prefix, n_layers=15):
         k = f"{prefix}{i}"
         out.append(torch.from_numpy(npz[k]) if k in npz.files else None)
     return out
+
+
+@contextlib.contextmanager
+def poisoned_empty():
+    """While active, every CUDA buffer created with torch.empty / torch.empty_like (the activations, saved tensors and
+    workspaces the host layer hands to the C-ABI uninitialised) is pre-filled with NaN bit patterns, so a kernel that
+    reads a location nothing wrote shows up as NaN downstream."""
+    e, el = torch.empty, torch.empty_like
+
+    def fill(t):
+        if t.is_cuda and t.numel():
+            if t.dtype == torch.uint8:
+                t.fill_(0xFF)
+            elif t.is_floating_point():
+                t.fill_(float("nan"))
+        return t
+
+    torch.empty = lambda *a, **k: fill(e(*a, **k))
+    torch.empty_like = lambda *a, **k: fill(el(*a, **k))
+    try:
+        yield
+    finally:
+        torch.empty, torch.empty_like = e, el
 
 
 def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:

@@ -134,3 +134,59 @@ def test_step3_iteration_fixture():
     np.testing.assert_allclose(np.array([float(g_kd[n].double().abs().sum()) for n in names_kd]), g["grad_abs_kd"], rtol=2e-3, atol=2e-6)
     delta = np.array([float((sd[str(k)].double() - sd0[str(k)].double()).abs().sum()) for k in g["after_names"]])
     np.testing.assert_allclose(delta, g["delta_abs"], rtol=2e-3, atol=2e-4)
+
+
+def test_multitask_iteration_against_torch_adam():
+    """oracle.multitask_iteration (train_multi_task.py:209-265 over the RAP network) against the real thing it
+    restates: torch.optim.Adam with the driver's two parameter groups stepping leaf tensors whose gradients come from
+    the same forward.  Covers the skip-tensors-without-gradient rule, the carried moments across visits, and that
+    running the visits one by one (``only=``) equals running the round at once."""
+    classes = [20, 20, 27]
+    sd0 = make_sd(classes, 30, 31)
+    gen = torch.Generator().manual_seed(600)
+    batches = [(torch.rand(1, 3, 32, 64, generator=gen), torch.randint(0, c, (1, 1, 32, 64), generator=gen)) for c in classes]
+    weights = [torch.tensor(w) for w in (oracle.WEIGHT_CITY, oracle.WEIGHT_BDD, oracle.WEIGHT_IDD)]
+    torch.manual_seed(77)
+    noises = [oracle.make_dropout_noise(1, True) for _ in classes]
+
+    sd_a = oracle.clone_sd(sd0)
+    losses_a = oracle.multitask_iteration(sd_a, batches, weights, noises)
+    sd_b, state_b, losses_b = oracle.clone_sd(sd0), {}, []
+    for ind in range(3):
+        losses_b += oracle.multitask_iteration(sd_b, batches, weights, noises, opt_state=state_b, only=[ind])
+    assert [float(x) for x in losses_a] == [float(x) for x in losses_b]
+    for k in sd_a:
+        assert torch.equal(sd_a[k], sd_b[k]), k
+
+    sd_c = oracle.clone_sd(sd0)
+    names = oracle.param_names(sd_c)
+    leaves = {n: sd_c[n].requires_grad_(True) for n in names}
+    opt = torch.optim.Adam([{"params": [leaves[n] for n in names if "encoder" in n], "lr": 5e-4 / 3},
+                            {"params": [leaves[n] for n in names if "decoder" in n]}], 5e-4, (0.9, 0.999), eps=1e-08,
+                           weight_decay=1e-4)
+    gmax = {}
+    for ind, (x, y) in enumerate(batches):
+        logits = oracle.net_forward(sd_c, x, ind, True, noises[ind])
+        opt.zero_grad()
+        loss = oracle.cross_entropy2d(logits, y[:, 0], weights[ind])
+        loss.backward()
+        for n in names:
+            if leaves[n].grad is not None:
+                gmax[n] = max(gmax.get(n, 0.0), float(leaves[n].grad.abs().max()))
+        opt.step()
+        assert abs(float(loss.detach()) - float(losses_a[ind])) <= 1e-6 * abs(float(loss.detach()))
+    moved, worst = 0, 0.0
+    for n in names:
+        ref_delta = (leaves[n].detach() - sd0[n]).abs().sum()
+        if float(ref_delta) == 0.0:
+            assert torch.equal(sd_a[n], sd0[n]), f"{n} must not move"
+        elif gmax[n] > 1e-6:        # a bias feeding a train-mode BatchNorm has a zero gradient: Adam amplifies its rounding noise
+            moved += 1
+            da, dc = (sd_a[n] - sd0[n]).double(), (leaves[n].detach() - sd0[n]).double()
+            # Adam's early steps are lr * g / (|g| + eps): an entry with a near-zero gradient turns summation-order noise into a
+            # full +-lr difference, so a few entries per tensor may disagree; all others must agree to 1e-6 (lr / 170)
+            off = int(((da - dc).abs() > 1e-6).sum())
+            worst = max(worst, off / da.numel())
+            assert off <= max(1, da.numel() // 100), f"{n}: {off} of {da.numel()} entries moved differently"
+    print("worst fraction of entries moving differently:", worst)
+    assert 0 < moved <= len(names)

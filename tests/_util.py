@@ -26,6 +26,20 @@ def make_sd(classes, init_seed, bn_seed):
     return oracle.perturb_bn_(sd, seed=bn_seed)
 
 
+def pretrained_sd(npz):
+    """State dict of tests/golden/pretrained_eval.npz (the reference's shipped trained weights, bf16-rounded, stored as
+    16-bit patterns; tests/golden/make_golden_pretrained.py) for Net([20], 1, 0)."""
+    import collections
+    sd = collections.OrderedDict()
+    for i, k in enumerate(str(s) for s in npz["keys"]):
+        a = npz[f"w{i}"]
+        if a.dtype == np.uint16:
+            sd[k] = torch.from_numpy((a.astype(np.int32) << 16)).view(torch.float32).clone()
+        else:
+            sd[k] = torch.from_numpy(np.asarray(a)).clone()
+    return sd
+
+
 def noise_list(npz, prefix, n_layers=15):
     out = []
     for i in range(n_layers):

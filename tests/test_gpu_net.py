@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from _util import assert_close, golden, make_sd, noise_list, oracle, poisoned_empty
+from _util import assert_close, golden, make_sd, noise_list, oracle, poisoned_empty, pretrained_sd
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-3
@@ -40,6 +40,61 @@ def test_eval_logits_match_reference(name):
         top2 = ref.topk(2, dim=1).values
         margin = (top2[:, 0] - top2[:, 1])[mism]
         assert float(margin.max()) < 1e-4, f"{int(mism.sum())} argmax mismatches with margin up to {float(margin.max())}"
+
+
+def test_pretrained_known_answer_eval():
+    """G1: the reference's shipped trained weights at BASELINE configs[0] (N=1, 128 x 256, 1 task, eval):
+    logits within 1e-3 of the reference's, class indices identical except at the reference's own near-ties."""
+    g = golden("pretrained_eval.npz")
+    net = _net([20], pretrained_sd(g)).eval()
+    h, w = (int(v) for v in g["hw"])
+    x = torch.rand(1, 3, h, w, generator=torch.Generator().manual_seed(int(g["x_seed"])))
+    with torch.no_grad():
+        y = net(x.to(DEV), 0)
+    ref = torch.from_numpy(g["logits"])
+    assert_close(y, ref, TOL, "pretrained logits")
+    mism = (y.argmax(1).cpu() != ref.argmax(1))
+    if mism.any():
+        top2 = ref.topk(2, dim=1).values
+        margin = (top2[:, 0] - top2[:, 1])[mism]
+        assert float(margin.max()) < 1e-3 and int(mism.sum()) <= 8, f"{int(mism.sum())} argmax mismatches, margin up to {float(margin.max())}"
+
+
+def test_pretrained_train_step_matches_oracle():
+    """Trained weights, train mode (batch statistics, dropout replayed, class-weighted CE): logits, loss and the
+    parameter gradients against the oracle at 2 x 64 x 128."""
+    from mdil_ss_b200.losses import CrossEntropyLoss2d
+    g = golden("pretrained_eval.npz")
+    sd = pretrained_sd(g)
+    net = _net([20], sd).train()
+    gen = torch.Generator().manual_seed(701)
+    x = torch.rand(2, 3, 64, 128, generator=gen)
+    labels = torch.randint(0, 20, (2, 16, 32), generator=gen).repeat_interleave(4, 1).repeat_interleave(4, 2)
+    torch.manual_seed(78)
+    noise = oracle.make_dropout_noise(2, True)
+    wts = torch.tensor(oracle.WEIGHT_CITY)
+    names = oracle.param_names(sd)
+    work = oracle._with_grad(oracle.clone_sd(sd), names)
+    ref_logits = oracle.net_forward(work, x, 0, True, noise)
+    ref_loss = oracle.cross_entropy2d(ref_logits, labels, wts)
+    ref_grads = dict(zip(names, torch.autograd.grad(ref_loss, [work[n] for n in names], allow_unused=True)))
+    logits = net(x.to(DEV), 0, drop_noise=_to_dev(noise))
+    loss = CrossEntropyLoss2d(wts).to(DEV)(logits, labels.to(DEV))
+    loss.backward()
+    assert_close(logits, ref_logits, TOL, "logits")
+    assert abs(float(loss) - float(ref_loss)) <= TOL * abs(float(ref_loss))
+    num = den = 0.0
+    for n, p in net.named_parameters():
+        r = ref_grads[n]
+        assert (p.grad is None) == (r is None), n
+        if r is None:
+            continue
+        num += float((p.grad.double().cpu() - r.double()).pow(2).sum())
+        den += float(r.double().pow(2).sum())
+        gs, rs = float(p.grad.double().abs().sum()), float(r.double().abs().sum())
+        if rs > 1e-3:
+            assert abs(gs - rs) <= 3e-2 * rs, f"{n}: sum|g| {gs} vs oracle {rs}"
+    assert (num / den) ** 0.5 <= 2e-2, f"all-parameter gradient relative L2 {(num / den) ** 0.5}"
 
 
 def test_train_forward_backward_matches_reference():

@@ -7,7 +7,7 @@ import os
 import numpy as np
 import torch
 
-from _util import GOLDEN, assert_close, golden, make_sd, noise_list, oracle
+from _util import GOLDEN, assert_close, golden, make_sd, noise_list, oracle, pretrained_sd
 
 TOL = 2e-5  # same ATen CPU kernels on both sides; only thread-count dependent summation order differs
 
@@ -44,6 +44,23 @@ def _train_inputs(g):
     x = torch.rand(2, 3, 32, 64, generator=gen)
     labels = torch.randint(0, 20, (2, 1, 32, 64), generator=gen)
     return x, labels
+
+
+def test_pretrained_known_answer_fixture():
+    """G1: the reference's shipped trained ERFNet weights; the fixture's logits come from the reference's
+    plain models/erfnet.py AND its RAP network with zero adapters (bit-identical, asserted by the generating script).
+    BASELINE configs[0] shape: N=1, 128 x 256, 1 task, eval forward."""
+    g = golden("pretrained_eval.npz")
+    sd = pretrained_sd(g)
+    assert len(sd) == 395
+    h, w = (int(v) for v in g["hw"])
+    x = torch.rand(1, 3, h, w, generator=torch.Generator().manual_seed(int(g["x_seed"])))
+    with torch.no_grad():
+        y = oracle.net_forward(sd, x, 0, False)
+    ref = torch.from_numpy(g["logits"])
+    assert_close(y, ref, TOL, "pretrained logits")
+    assert float(ref.max() - ref.min()) > 15.0                  # a trained network's logit range, not a random-init one
+    assert int((y.argmax(1) != ref.argmax(1)).sum()) == 0
 
 
 def test_train_forward_backward_fixture():

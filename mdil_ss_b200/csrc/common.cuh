@@ -38,6 +38,16 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 
 constexpr int kNumSMs = 148;  // B200
 
+// Launch-time state that belongs to a DEVICE (function attributes, occupancy answers): the library may be driven from
+// several host threads for several devices of one process (nn.DataParallel, train_new_task_step2.py:473-475), so a
+// plain function-level static would leave every device but the first unconfigured.  Races are benign (idempotent).
+constexpr int kMaxDevices = 64;
+static inline int current_device_slot() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev >= 0 && dev < kMaxDevices ? dev : 0;
+}
+
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float4 make4(float v) { return make_float4(v, v, v, v); }
 

@@ -6,6 +6,8 @@
 // (models/erfnet_RA_parallel.py:17,23), the UpsamplerBlock 3x3 stride-2 transposed conv as four
 // sub-pixel parity classes with 1/2/2/4 taps and its dgrad (:155-156), and every weight gradient.
 // FP32 FFMA register-tiled GEMM (8x4 / TMxTN per thread), operands staged through shared memory.
+#include <atomic>
+
 #include "kernels.cuh"
 
 #include <stdlib.h>
@@ -283,10 +285,11 @@ static int conv_mma_launch(const ConvGeom& g, const float* A, const float* Wp, c
   for (int c = 0; c < g.nclasses; ++c) total_taps += g.cls[c].ntaps;
   const size_t smem = (size_t)total_taps * g.CIN * CM_WP * sizeof(float);
   MDIL_REQUIRE(smem <= 100 * 1024, "conv_mma: weight slice too large");
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<bool> attr_set[kMaxDevices];
+  std::atomic<bool>& done = attr_set[current_device_slot()];
+  if (!done.load(std::memory_order_acquire)) {
     MDIL_CUDA(cudaFuncSetAttribute(conv_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    attr_set = true;
+    done.store(true, std::memory_order_release);
   }
   const size_t P = (size_t)g.N * g.VH * g.VW;
   const size_t ntiles = (P + 15) / 16;

@@ -19,6 +19,8 @@
 //   * the epilogues read TMEM with the 16x256b shape (four lanes own 32 contiguous bytes of a pixel row): their inputs
 //     (ReLU masks, p, dy, y; prefetched before the accumulator is waited for) and results use sector-filling 8-byte
 //     global accesses without shared-memory staging; per-channel BatchNorm sums: warp shuffles -> shared -> fp64 atomics.
+#include <atomic>
+
 #include "kernels.cuh"
 
 #include <stdio.h>
@@ -704,7 +706,9 @@ int launch_c(const PairArgs& a, cudaStream_t s) {
   MDIL_REQUIRE(total > 0 && total < (1L << 30), "pair_tc3: tile count");
   MDIL_REQUIRE(a.wstream_tc != nullptr && ((uintptr_t)a.wstream_tc & 15) == 0, "pair_tc3: weight stream");
   const int cl = cluster_size();
-  static int max_ctas = 0;   // co-resident CTAs (1 per SM by shared memory), in whole clusters
+  static std::atomic<int> max_ctas_dev[kMaxDevices];   // co-resident CTAs (1 per SM by shared memory), in whole clusters
+  std::atomic<int>& max_ctas_slot = max_ctas_dev[current_device_slot()];
+  int max_ctas = max_ctas_slot.load(std::memory_order_acquire);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cudaLaunchAttribute attr[1];
@@ -727,6 +731,7 @@ int launch_c(const PairArgs& a, cudaStream_t s) {
     MDIL_REQUIRE(n >= cl, "pair_tc3: no co-resident cluster fits");
     if (n > kNumSMs) n = kNumSMs / cl * cl;
     max_ctas = n;
+    max_ctas_slot.store(n, std::memory_order_release);
   }
   long grid = total < max_ctas ? (total + cl - 1) / cl * cl : max_ctas;
   Geo geo;

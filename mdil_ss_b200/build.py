@@ -16,7 +16,7 @@ OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libmdil_b200.so")
 SOURCES = ["elementwise.cu", "conv_taps.cu", "nb1d_pair.cu", "nb1d_pair_tc.cu", "nb1d_pair_tc3.cu", "wgrad_tc.cu", "head_loss.cu", "api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "--use_fast_math=false"]
+              "-Xcompiler", "-fPIC"]          # no --use_fast_math: fp32 parity with the reference
 
 
 def _nvcc() -> str:
@@ -38,7 +38,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
     headers = [os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith((".cuh", ".h"))]
     headers.append(os.path.join(HERE, "..", "include", "mdil_b200.h"))
-    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    flags = list(NVCC_FLAGS)
     jobs = []
     for src in SOURCES:
         s = os.path.join(CSRC, src)

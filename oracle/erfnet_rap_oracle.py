@@ -456,6 +456,36 @@ def clone_sd(sd: SD) -> SD:
     return type(sd)((k, v.detach().clone()) for k, v in sd.items())
 
 
+def multitask_sd_as_rap(sd_mt: SD, nb_tasks: int) -> SD:
+    """models/erfnet_multi_task.py restated through the RAP restatement: its Net (:150-163) is the RAP network with
+    ONE BatchNorm per position shared by all domains (``bn`` / ``bn1`` / ``bn2``, :18,36,44 -> ``bn_ini.t`` /
+    ``bns_1.t`` / ``bns_2.t`` for every t, the same tensors) and no adapters (zero ``parallel_conv``), with the same
+    encoder Dropout2d (:83-92).  The returned dict ALIASES the multi-task tensors, so train-mode running-statistic
+    updates and autograd leaves are shared with ``sd_mt``."""
+    import collections
+    out: SD = collections.OrderedDict()
+    for k, v in sd_mt.items():
+        if k.startswith("decoder."):
+            out[k] = v
+            continue
+        done = False
+        for src, dst in ((".bn1.", ".bns_1."), (".bn2.", ".bns_2."), (".bn.", ".bn_ini.")):
+            if src in k:
+                for t in range(nb_tasks):
+                    out[k.replace(src, f"{dst}{t}.")] = v
+                done = True
+                break
+        if not done:
+            out[k] = v
+    for i, (kind, ch, _p, _d) in enumerate(ENCODER_LAYERS):
+        if kind == "rap":
+            for which in (1, 2):
+                for t in range(nb_tasks):
+                    out[f"encoder.layers.{i}.parallel_conv_{which}.{t}.weight"] = torch.zeros(ch, ch, 1, 1)
+                    out[f"encoder.layers.{i}.parallel_conv_{which}.{t}.bias"] = torch.zeros(ch)
+    return out
+
+
 # ------------------------------------------------------------------------ metric
 def iou_add_batch(pred: torch.Tensor, gt: torch.Tensor, n_classes: int, ignore_index: int):
     """iouEval.addBatch — iouEval.py:21-70, for index inputs [N,1,H,W]: one-hot both, drop the ignore channel,

@@ -53,6 +53,10 @@ NB1D_CASES = [
     (128, 16, True, 1, 16, 32, 0.3),
     (128, 16, True, 2, 64, 128, 0.3),
     (128, 1, True, 1, 7, 5, 0.0),
+    # adapter-off blocks WITH dropout and dilation: the encoder of the multi-task joint model (models/erfnet_multi_task.py:83-92)
+    (64, 1, False, 2, 9, 37, 0.03),
+    (128, 4, False, 1, 16, 32, 0.3),
+    (128, 16, False, 2, 11, 19, 0.3),
 ]
 
 

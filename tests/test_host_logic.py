@@ -206,3 +206,36 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["higher_is_better"] is True and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_lr_factor_follows_lambda_lr():
+    """FlatAdam.set_lr_factor(poly_lr_factor(epoch, E)) against the drivers' scheduler (train_new_task_step2.py:244-245,
+    254: LambdaLR(optimizer, lambda1), scheduler.step(epoch)) on torch.optim.Adam with the same two groups, including a
+    step taken under the decayed rates."""
+    import warnings
+    from mdil_ss_b200 import train_step as T
+    from mdil_ss_b200.parallel import FlatAdam
+    torch.manual_seed(1)
+    ws = [torch.randn(6, 2), torch.randn(7)]
+    pa = [torch.nn.Parameter(w.clone()) for w in ws]
+    pb = [torch.nn.Parameter(w.clone()) for w in ws]
+    fa = FlatAdam([{"params": pa[:1], "lr": 5e-6}, {"params": pa[1:]}], 5e-4)
+    ta = torch.optim.Adam([{"params": pb[:1], "lr": 5e-6}, {"params": pb[1:]}], 5e-4, (0.9, 0.999), eps=1e-8, weight_decay=1e-4)
+    num_epochs = 150
+    sched = torch.optim.lr_scheduler.LambdaLR(ta, lr_lambda=lambda epoch: pow((1 - ((epoch - 1) / num_epochs)), 0.9))
+    for epoch in (1, 2, 75, 150):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")                      # the epoch argument is deprecated in torch, the drivers use it
+            sched.step(epoch)
+        fa.set_lr_factor(T.poly_lr_factor(epoch, num_epochs))
+        assert [g["lr"] for g in fa.groups] == pytest.approx([g["lr"] for g in ta.param_groups], rel=1e-12)
+        grads = [torch.randn_like(w) for w in ws]
+        fa.zero_grad()
+        ta.zero_grad()
+        for p, q, g in zip(pa, pb, grads):
+            p.grad.copy_(g)
+            q.grad = g.clone()
+        fa.step(allreduce=False)
+        ta.step()
+        for p, q in zip(pa, pb):
+            assert torch.allclose(p, q, rtol=1e-6, atol=1e-8)

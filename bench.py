@@ -37,6 +37,7 @@ def parse():
     ap.add_argument("--full-res", action="store_true", help="1024x2048 crops (BASELINE config 5) instead of 512x1024")
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="crops per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the PyTorch-eager (cuDNN) baseline leg")
     ap.add_argument("--ncu-step", action="store_true",
                     help="profiling aid: after warm-up run ONE step between cudaProfilerStart/Stop and exit "
                          "(use with ncu --profile-from-start off); prints no bench line")
@@ -172,6 +173,58 @@ def time_cpu(workload, n, steps, warmup):
         step()
     dt = time.perf_counter() - t0
     return n * steps / dt, dt / steps * 1e3, cores
+
+
+def time_gpu_eager(n, steps, warmup, allow_tf32, dev):
+    """Like-for-like GPU baseline: the reference ALGORITHM as the reference runs it on a
+    GPU -- PyTorch eager, ATen/cuDNN convolutions and batch norm, NCHW fp32, cudnn.benchmark off (the drivers never set
+    it), F.nll_loss(F.log_softmax) as CrossEntropyLoss2d (train_new_task_step2.py:84-92), torch.optim.Adam as the drivers
+    configure it (:237-239) -- on the same B200, same synthetic step-1 batch.  Functional restatement = the oracle port
+    moved to the device (the unmodified reference files do not exist on the GPU box)."""
+    import torch
+    import torch.nn.functional as F
+    from oracle import erfnet_rap_oracle as oracle
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = bool(allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = bool(allow_tf32)
+    try:
+        g = torch.Generator().manual_seed(1234)
+        images = torch.rand(n, 3, H, W, generator=g).to(dev)
+        labels = (torch.randint(0, NCLS, (n, H // 32, W // 32), generator=g)
+                  .repeat_interleave(32, 1).repeat_interleave(32, 2).contiguous().to(dev))
+        weight = torch.tensor(oracle.WEIGHT_CITY, device=dev)
+        sd = {k: v.to(dev) for k, v in oracle.init_state_dict([NCLS], 1, seed=0).items()}
+        names = oracle.param_names(sd)
+        for k in names:
+            sd[k].requires_grad_(True)
+        opt = torch.optim.Adam([sd[k] for k in names], 5e-4, (0.9, 0.999), eps=1e-08, weight_decay=1e-4)
+
+        def step():
+            # Dropout2d noise drawn on the device, as F.dropout2d does inside the reference's blocks
+            noise = [torch.empty(n, ch, 1, 1, device=dev).bernoulli_(1 - p).div_(1 - p) if kind == "rap" and p != 0 else None
+                     for kind, ch, p, _ in oracle.ENCODER_LAYERS]
+            logits = oracle.net_forward(sd, images, 0, True, noise)
+            opt.zero_grad()
+            loss = F.nll_loss(F.log_softmax(logits, dim=1), labels, weight)
+            loss.backward()
+            opt.step()
+            return loss
+
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        del sd, opt
+        torch.cuda.empty_cache()
+        return n * 1e3 / ms, ms
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
 
 
 def run_reference(args):
@@ -373,6 +426,21 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{cpu_steps} timed + 1 warm-up iterations of the same step at batch 1 on the host CPU "
                                               f"({ms:.0f} ms/iteration)"}
+        if not args.no_gpu_baseline and world == 1 and args.workload == "step1" and not args.full_res:
+            # like-for-like GPU baseline: the same step in PyTorch eager (ATen/cuDNN) on this B200, fp32 and TF32
+            gb = {"kind": "reference algorithm (oracle port) on cuda: PyTorch eager, ATen/cuDNN NCHW, torch.optim.Adam; "
+                          "cudnn.benchmark off as in the drivers", "unit": UNIT, "batch": n, "warmup": 10, "steps": 20}
+            try:
+                for tf32 in (False, True):
+                    v, ms = time_gpu_eager(n, 20, 10, tf32, dev)
+                    gb["allow_tf32=%s" % tf32] = {"value": v, "ms_per_step": ms}
+                gb["value"] = gb["allow_tf32=False"]["value"]
+                gb["allow_tf32"] = False
+                gb["speedup_vs_fp32_eager"] = value / gb["allow_tf32=False"]["value"]
+                gb["speedup_vs_tf32_eager"] = value / gb["allow_tf32=True"]["value"]
+            except Exception as exc:   # the baseline must never take the bench line down
+                gb["error"] = repr(exc)[:300]
+            line["gpu_baseline"] = gb
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -72,10 +72,17 @@ def _bn_struct(w, b, rm, rv) -> L.BnParams:
 
 
 class PackedCache:
-    """Kernel-friendly copies of a block's weights, refreshed when a parameter's version or storage changes."""
+    """Kernel-friendly copies of a block's weights, refreshed when a parameter's version or storage changes.
+
+    ``tensor._version`` does not move under every in-place update (``dist.broadcast(p)``, ``p.data.mul_()``,
+    ``dist.all_reduce(p.data)`` leave it unchanged): code that rewrites weights that way must call
+    :func:`invalidate_packed` on the module (``parallel.broadcast_module`` and the checkpoint helpers do)."""
 
     def __init__(self) -> None:
         self._entries = {}
+
+    def invalidate(self) -> None:
+        self._entries.clear()
 
     def get(self, key, tensors: Sequence[torch.Tensor], nfloats: int, pack_fn) -> torch.Tensor:
         sig = tuple((t.data_ptr(), t._version) for t in tensors)
@@ -88,6 +95,15 @@ class PackedCache:
             self._entries[key] = (sig, buf)
             return buf
         return ent[1]
+
+
+def invalidate_packed(module: torch.nn.Module) -> None:
+    """Drop every packed weight copy held under ``module`` (call after any weight update that does not go through
+    autograd-visible in-place ops or FlatAdam: ``.data`` writes, collectives on parameters, custom EMA / clipping)."""
+    for m in module.modules():
+        cache = getattr(m, "_cache", None)
+        if isinstance(cache, PackedCache):
+            cache.invalidate()
 
 
 # ======================================================================================= nb1d
@@ -432,6 +448,9 @@ class CrossEntropy2dFn(torch.autograd.Function):
         lib = L.lib()
         dlogits, acc = ctx.internal
         if dlogits is None:
+            if ctx.needs_input_grad[0]:
+                raise RuntimeError("cross_entropy2d: the fused logit gradient is single-use (scaled in place); a second "
+                                   "backward through the same loss (retain_graph=True) is not supported")
             return None, None, None, None
         ctx.internal = (None, None)  # single use: the stash is scaled in place
         with torch.cuda.device_of(dlogits):
@@ -469,6 +488,9 @@ class OutputKDFn(torch.autograd.Function):
         lib = L.lib()
         dstudent = ctx.internal
         if dstudent is None:
+            if ctx.needs_input_grad[0]:
+                raise RuntimeError("output_kd: the fused student gradient is single-use (scaled in place); a second "
+                                   "backward through the same loss (retain_graph=True) is not supported")
             return None, None
         ctx.internal = None
         with torch.cuda.device_of(dstudent):

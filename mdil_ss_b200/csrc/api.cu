@@ -25,8 +25,8 @@ int pair_impl_mode() {
   static const int mode = [] {
     const char* e = getenv("MDIL_PAIR_IMPL");
     if (e != nullptr && strcmp(e, "ffma") == 0) return 0;
-    if (e != nullptr && strcmp(e, "tc2") == 0) return 2;
-    return 3;
+    if (e != nullptr && strcmp(e, "tc3") == 0) return 3;
+    return 4;
   }();
   return mode;
 }
@@ -147,7 +147,9 @@ static bool use_tc_wgrad(int C) {
   return mode == 1 && (C == 64 || C == 128);
 }
 static inline const float* tc_stream(const float* packed, int C, int which) {
-  return use_tensor_cores(C) ? packed + (size_t)28 * C * C + (size_t)which * 14 * C * C : nullptr;
+  if (!use_tensor_cores(C)) return nullptr;
+  // tc3: four streams of 14 C^2 floats (hi/lo TF32 images); h3: four streams of 14 C^2 16-bit values (= 7 C^2 floats)
+  return packed + (size_t)28 * C * C + (size_t)which * (pair_impl_mode() == 4 ? 7 : 14) * C * C;
 }
 
 size_t mdil_nb1d_fwd_workspace_bytes(const mdil_nb1d_desc* d) { return 256 + (size_t)4 * d->C * sizeof(double) + 256; }
@@ -170,7 +172,8 @@ int mdil_nb1d_pack(const mdil_nb1d_desc* d, const mdil_nb1d_weights* w, float* p
   const float* w6[6] = {w->w31_1, w->w13_1, w->w31_2, w->w13_2, w->wp1, w->wp2};
   const bool tc = use_tensor_cores(C);
   (void)CC;
-  MDIL_TRY(launch_pack_block(w6, packed, C, d->has_adapter, tc ? 0 : 1, tc ? pair_impl_mode() : 0, s));
+  if (tc && pair_impl_mode() == 4) return launch_pack_block_h3(w6, packed + (size_t)28 * C * C, C, d->has_adapter, s);
+  MDIL_TRY(launch_pack_block(w6, packed, C, d->has_adapter, tc ? 0 : 1, tc ? 3 : 0, s));
   return 0;
 }
 

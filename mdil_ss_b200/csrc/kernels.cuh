@@ -87,7 +87,7 @@ struct PairArgs {
   const float* in_scale;   // nullable: prologue v = relu(v*scale+shift)
   const float* in_shift;
   const float* wstream;    // packed [3][C][C] first conv, [3][C][C] second conv, [C][C] adapter (if has_adapter)
-  const float* wstream_tc; // tensor-core path: hi/lo SWIZZLE_64B chunk images (conv 1, adapter, conv 2) or NULL
+  const float* wstream_tc; // tensor-core path: hi/lo SWIZZLE_64B chunk images (16-bit for h3, TF32 for tc3) or NULL
   const float* b1;         // nullable
   const float* b2;         // nullable
   const float* bad;        // nullable (adapter bias)
@@ -104,14 +104,14 @@ struct PairArgs {
 };
 int launch_pair(const PairArgs& a, cudaStream_t s);          // dispatch: tensor-core kernel when wstream_tc != NULL
 int launch_pair_ffma(const PairArgs& a, cudaStream_t s);     // nb1d_pair.cu (FP32 FFMA; all C)
-int launch_pair_tc(const PairArgs& a, cudaStream_t s);       // nb1d_pair_tc.cu (tcgen05 3xTF32; C = 64, 128)
-int launch_pack_tc(const float* src_stream, float* dst_stream, int C, int has_adapter, cudaStream_t s);
-int launch_pair_tc3(const PairArgs& a, cudaStream_t s);      // nb1d_pair_tc3.cu (persistent pipelined tcgen05 kernel; default)
+int launch_pair_h3(const PairArgs& a, cudaStream_t s);       // nb1d_pair_h3.cu (tcgen05 kind::f16, fp16/bf16 split operands; default)
+int launch_pack_block_h3(const float* const* w6, void* packed, int C, int has_adapter, cudaStream_t s);
+int launch_pair_tc3(const PairArgs& a, cudaStream_t s);      // nb1d_pair_tc3.cu (persistent pipelined 3xTF32 tcgen05 kernel; A/B)
 int launch_pack_tc3(const float* src_stream, float* dst_stream, int C, int has_adapter, cudaStream_t s);
-// one launch: fp32 FFMA streams (write_fp32) and/or tensor-core images (tc_order 0 = none, 2, 3) of a whole block
+// one launch: fp32 FFMA streams (write_fp32) and/or 3xTF32 tensor-core images (tc_order 0 = none, 3) of a whole block
 int launch_pack_block(const float* const* w6, float* packed, int C, int has_adapter, int write_fp32, int tc_order,
                       cudaStream_t s);
-int pair_impl_mode();   // MDIL_PAIR_IMPL: 0 = "ffma", 2 = "tc2" (one tile per CTA), 3 = pipelined tensor-core kernel (default)
+int pair_impl_mode();   // MDIL_PAIR_IMPL: 0 = "ffma", 3 = "tc3" (3xTF32 tensor-core kernel), 4 = 16-bit split tensor-core kernel (default)
 void pair_profile_record_begin(const PairArgs& a, cudaStream_t s, void** rec);
 void pair_profile_record_end(cudaStream_t s, void* rec);
 int pair_profile_begin();

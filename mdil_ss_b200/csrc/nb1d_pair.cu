@@ -478,7 +478,7 @@ int launch_pair(const PairArgs& a_in, cudaStream_t s) {
   void* rec = nullptr;
   pair_profile_record_begin(a, s, &rec);
   const bool tc = a.wstream_tc != nullptr && (a.C == 64 || a.C == 128);
-  const int rc = !tc ? launch_pair_ffma(a, s) : (pair_impl_mode() == 3 ? launch_pair_tc3(a, s) : launch_pair_tc(a, s));
+  const int rc = !tc ? launch_pair_ffma(a, s) : (pair_impl_mode() == 3 ? launch_pair_tc3(a, s) : launch_pair_h3(a, s));
   pair_profile_record_end(s, rec);
   return rc;
 }

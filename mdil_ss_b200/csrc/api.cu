@@ -136,7 +136,10 @@ int mdil_nchw_to_nhwc4(const float* x, float* y, int N, int C, int H, int W, voi
 
 // =============================================================================== nb1d
 // [0, 28 C^2): fp32 streams of the FFMA kernel; [28 C^2, 84 C^2): hi/lo images of the tensor-core kernel (4 x 14 C^2)
-size_t mdil_nb1d_packed_floats(int C) { return (size_t)84 * C * C; }
+// C = 16: [0, 28 C^2) fp32 streams (FFMA kernel), then the packed-4 images (4 streams x 14 x 64^2 16-bit values) and the
+// four conv biases replicated per pixel slot (float [4][64])
+static const size_t kP4ImgFloats = (size_t)4 * 14 * 64 * 64 / 2;
+size_t mdil_nb1d_packed_floats(int C) { return C == 16 ? (size_t)28 * 256 + kP4ImgFloats + 256 : (size_t)84 * C * C; }
 
 static bool use_tensor_cores(int C) { return pair_impl_mode() != 0 && (C == 64 || C == 128); }
 static bool use_tc_wgrad(int C) {
@@ -152,13 +155,36 @@ static inline const float* tc_stream(const float* packed, int C, int which) {
   return packed + (size_t)28 * C * C + (size_t)which * (pair_impl_mode() == 4 ? 7 : 14) * C * C;
 }
 
-size_t mdil_nb1d_fwd_workspace_bytes(const mdil_nb1d_desc* d) { return 256 + (size_t)4 * d->C * sizeof(double) + 256; }
+// Packed-4 view of the C = 16 blocks (decoder non_bottleneck_1d: no adapter, dilation 1): [N,H,W,16] is read as
+// [N,H,W/4,64] and the block runs on the C = 64 tensor-core kernels with block-structured 64x64 tap matrices
+// (nb1d_pair_h3.cu: pack_block_p4_kernel).  MDIL_P4=0 keeps the FFMA / mma.sync kernels for A/B measurements.
+static bool p4_enabled() {
+  static const int on = [] {
+    const char* e = getenv("MDIL_P4");
+    return (e != nullptr && strcmp(e, "0") == 0) ? 0 : 1;
+  }();
+  return on == 1 && pair_impl_mode() == 4;
+}
+static bool p4_ok(const mdil_nb1d_desc* d) {
+  return d->C == 16 && p4_enabled() && !d->has_adapter && d->dil == 1 && d->W % 4 == 0;
+}
+
+size_t mdil_nb1d_fwd_workspace_bytes(const mdil_nb1d_desc* d) {
+  const int Cs = d->C == 16 ? 64 : d->C;     // packed-4 view: sums per (pixel slot, channel)
+  return 256 + (size_t)4 * Cs * sizeof(double) + (size_t)4 * Cs * sizeof(float) + 512;
+}
 
 size_t mdil_nb1d_bwd_workspace_bytes(const mdil_nb1d_desc* d) {
   size_t T = align_up((size_t)d->N * d->H * d->W * d->C * sizeof(float), 256);
-  return 3 * T + (size_t)4 * d->C * sizeof(double) + (size_t)6 * d->C * sizeof(float) +
-         ((size_t)18 * d->C * d->C + 6 * d->C) * sizeof(float) + 10 * 256;   // 6 accumulators [3][C][C] + 6 bias sums [C]
+  const int Cw = d->C == 16 ? 64 : d->C;     // packed-4 view: weight-gradient accumulators of the 64-channel view
+  return 3 * T + (size_t)4 * Cw * sizeof(double) + (size_t)6 * d->C * sizeof(float) + (size_t)4 * Cw * sizeof(float) +
+         ((size_t)18 * Cw * Cw + 6 * Cw) * sizeof(float) + 12 * 256;   // 6 accumulators [3][C][C] + 6 bias sums [C]
 }
+
+static inline const float* p4_stream(const float* packed, int which) {
+  return packed + (size_t)28 * 256 + (size_t)which * 7 * 64 * 64;
+}
+static inline const float* p4_bias(const float* packed, int k) { return packed + (size_t)28 * 256 + kP4ImgFloats + (size_t)k * 64; }
 
 int mdil_nb1d_pack(const mdil_nb1d_desc* d, const mdil_nb1d_weights* w, float* packed, void* stream) {
   MDIL_TRY(check_nb1d(d));
@@ -174,7 +200,43 @@ int mdil_nb1d_pack(const mdil_nb1d_desc* d, const mdil_nb1d_weights* w, float* p
   (void)CC;
   if (tc && pair_impl_mode() == 4) return launch_pack_block_h3(w6, packed + (size_t)28 * C * C, C, d->has_adapter, s);
   MDIL_TRY(launch_pack_block(w6, packed, C, d->has_adapter, tc ? 0 : 1, tc ? 3 : 0, s));
+  if (C == 16 && p4_enabled() && !d->has_adapter) {   // both forms: the launch picks the packed-4 path per shape (W % 4, dil)
+    const float* w4[4] = {w->w31_1, w->w13_1, w->w31_2, w->w13_2};
+    const float* b4[4] = {w->b31_1, w->b13_1, w->b31_2, w->b13_2};
+    MDIL_TRY(launch_pack_block_p4(w4, b4, packed + (size_t)28 * 256, packed + (size_t)28 * 256 + kP4ImgFloats, s));
+  }
   return 0;
+}
+
+// C = 16 block on the packed-4 view (see p4_ok): same sequence as mdil_nb1d_fwd with C = 64, W/4 pair launches; the
+// per-channel BatchNorm sums arrive per (pixel slot, channel) and are folded by the finalize kernel
+static int nb1d_fwd_p4(const mdil_nb1d_desc* d, const float* x, const mdil_nb1d_weights* w, const float* packed,
+                       const float* drop_mask, float* y, const mdil_nb1d_saved* sv, void* ws, cudaStream_t s) {
+  const int C = 16, CP = 64;
+  const size_t HW = (size_t)d->H * d->W;
+  const double count = (double)d->N * (double)HW;
+  Carver cv(ws);
+  double* sums1 = cv.take<double>(4 * CP);     // [2][2][64]
+  double* sums2 = sums1 + 2 * CP;
+  float* rep1 = cv.take<float>(4 * CP);         // BN1 statistics replicated per pixel slot [4][64]
+  float* st1 = sv->stats;
+  float* st2 = sv->stats + 4 * C;
+  if (d->train) MDIL_CUDA(cudaMemsetAsync(sums1, 0, 4 * CP * sizeof(double), s));
+  PairArgs a;
+  memset(&a, 0, sizeof(a));
+  a.N = d->N; a.H = d->H; a.W = d->W / 4; a.C = CP; a.has_adapter = 0; a.vert_first = 1; a.epi = kEpiFwd; a.dil = 1; a.view_c = C;
+  a.in = x; a.wstream_tc = p4_stream(packed, 0); a.b1 = p4_bias(packed, 0); a.b2 = p4_bias(packed, 1);
+  a.mid_out = d->save ? sv->a : nullptr; a.out = sv->p; a.sums = d->train ? sums1 : nullptr;
+  MDIL_TRY(launch_pair(a, s));
+  MDIL_TRY(launch_bn_finalize(sums1, CP, count, C, w->bn1.weight, w->bn1.bias, w->bn1.running_mean, w->bn1.running_var,
+                              d->eps, d->momentum, d->train, st1, s, 4, rep1));
+  a.in = sv->p; a.in_scale = rep1 + 2 * CP; a.in_shift = rep1 + 3 * CP; a.wstream_tc = p4_stream(packed, 1);
+  a.b1 = p4_bias(packed, 2); a.b2 = p4_bias(packed, 3);
+  a.mid_out = d->save ? sv->c : nullptr; a.out = sv->s; a.sums = d->train ? sums2 : nullptr;
+  MDIL_TRY(launch_pair(a, s));
+  MDIL_TRY(launch_bn_finalize(sums2, CP, count, C, w->bn2.weight, w->bn2.bias, w->bn2.running_mean, w->bn2.running_var,
+                              d->eps, d->momentum, d->train, st2, s, 4, nullptr));
+  return launch_bn_act(sv->s, st2, drop_mask, x, y, d->N, HW, C, s);
 }
 
 int mdil_nb1d_fwd(const mdil_nb1d_desc* d, const float* x, const mdil_nb1d_weights* w, const float* packed,
@@ -182,6 +244,7 @@ int mdil_nb1d_fwd(const mdil_nb1d_desc* d, const float* x, const mdil_nb1d_weigh
   MDIL_TRY(check_nb1d(d));
   MDIL_REQUIRE(ws_bytes >= mdil_nb1d_fwd_workspace_bytes(d), "nb1d_fwd: workspace too small");
   MDIL_REQUIRE(sv != nullptr && sv->p != nullptr && sv->s != nullptr && sv->stats != nullptr, "nb1d_fwd: p/s/stats buffers required");
+  if (p4_ok(d)) return nb1d_fwd_p4(d, x, w, packed, drop_mask, y, sv, ws, S(stream));
   const int C = d->C;
   const long CC = (long)C * C;
   const size_t HW = (size_t)d->H * d->W;
@@ -243,6 +306,78 @@ static int nb1d_wgrad(const mdil_nb1d_desc* d, int dil, bool vert, int taps, con
   return launch_wgrad_taps(g, A, sc, sh, G, dW, s_ci, s_co, s_t, db, s);
 }
 
+// one weight gradient of the packed-4 view through wgrad_tc<64>; its [3][64][64] accumulator is folded back by `ul`
+static int nb1d_wgrad_p4(const mdil_nb1d_desc* d, bool vert, const float* A, const float* sc, const float* sh, const float* G,
+                         float* dW, float* db, float* acc, float* bacc, UnpackP4List* ul, cudaStream_t s) {
+  if (dW == nullptr) {
+    MDIL_REQUIRE(db == nullptr, "nb1d_bwd: bias gradient without weight gradient is not supported");
+    return 0;
+  }
+  WgradTcArgs w;
+  memset(&w, 0, sizeof(w));
+  w.A = A; w.a_scale = sc; w.a_shift = sh; w.G = G; w.dWacc = acc; w.db = db != nullptr ? bacc : nullptr;
+  w.N = d->N; w.H = d->H; w.W = d->W / 4; w.C = 64; w.dil = 1; w.ntaps = 3; w.vert = vert ? 1 : 0;
+  MDIL_TRY(launch_wgrad_tc(w, s));
+  UnpackP4Item& it = ul->item[ul->n++];
+  it.acc = acc; it.dW = dW; it.dbacc = bacc; it.db = db; it.horizontal = vert ? 0 : 1;
+  return 0;
+}
+
+static int nb1d_bwd_p4(const mdil_nb1d_desc* d, const float* dy, const float* x, const float* y, const mdil_nb1d_weights* w,
+                       const float* packed, const float* drop_mask, const mdil_nb1d_saved* sv, float* dx,
+                       const mdil_nb1d_grads* gr, void* ws, cudaStream_t s) {
+  const int C = 16, CP = 64, N = d->N, H = d->H, W = d->W;
+  const size_t HW = (size_t)H * W;
+  const size_t T = (size_t)N * HW * C;
+  const double count = (double)N * (double)HW;
+  Carver cv(ws);
+  double* sums2 = cv.take<double>(2 * C + 2 * CP);   // BN2 backward sums [2][16], then BN1's per (slot, channel) [2][64]
+  double* sums1 = sums2 + 2 * C;
+  float* coef2 = cv.take<float>(3 * C);
+  float* coef1 = cv.take<float>(3 * C);
+  float* rep1 = cv.take<float>(4 * CP);
+  float* T1 = cv.take<float>(T);
+  float* T2 = cv.take<float>(T);
+  float* T3 = cv.take<float>(T);
+  const size_t WS = (size_t)3 * CP * CP;
+  float* wacc = cv.take<float>(4 * WS + 4 * CP);     // four accumulators [3][64][64], then four bias sums [64]
+  float* bacc = wacc + 4 * WS;
+  UnpackP4List ul;
+  ul.n = 0;
+  MDIL_CUDA(cudaMemsetAsync(wacc, 0, sizeof(float) * (4 * WS + 4 * CP), s));
+  MDIL_CUDA(cudaMemsetAsync(sums2, 0, (2 * C + 2 * CP) * sizeof(double), s));
+  const float* st1 = sv->stats;
+  const float* st2 = sv->stats + 4 * C;
+  MDIL_TRY(launch_replicate_stats(st1, rep1, C, 4, s));
+
+  // ---- BN2 backward (+ ReLU mask of y, dropout): ds  (elementwise kernels on the 16-channel view)
+  MDIL_TRY(launch_bn_bwd_stats(dy, y, drop_mask, sv->s, st2, sums2, N, HW, C, s));
+  MDIL_TRY(launch_bn_bwd_finalize(sums2, count, C, w->bn2.weight, st2, coef2, gr->bn2_w, gr->bn2_b, s));
+  MDIL_TRY(launch_bn_bwd_apply(dy, y, drop_mask, sv->s, st2, coef2, T1, N, HW, C, s));
+
+  // ---- pair 2 backward: ds -> dc' -> dq (masked by r>0), sums for BN1 backward
+  PairArgs a;
+  memset(&a, 0, sizeof(a));
+  a.N = N; a.H = H; a.W = W / 4; a.C = CP; a.has_adapter = 0; a.vert_first = 0; a.dil = 1; a.view_c = C;
+  a.in = T1; a.wstream_tc = p4_stream(packed, 2); a.mid_mask = sv->c; a.mid_out = T2; a.out = T3;
+  a.epi = kEpiBwdMaskStats; a.e0 = sv->p; a.e_stats = rep1; a.sums = sums1;
+  MDIL_TRY(launch_pair(a, s));
+  MDIL_TRY(nb1d_wgrad_p4(d, false, sv->c, nullptr, nullptr, T1, gr->w13_2, gr->b13_2, wacc + 0 * WS, bacc + 0 * CP, &ul, s));
+  MDIL_TRY(nb1d_wgrad_p4(d, true, sv->p, rep1 + 2 * CP, rep1 + 3 * CP, T2, gr->w31_2, gr->b31_2, wacc + 1 * WS, bacc + 1 * CP, &ul, s));
+
+  // ---- BN1 backward: dq -> dp (overwrites ds)
+  MDIL_TRY(launch_bn_bwd_finalize(sums1, count, C, w->bn1.weight, st1, coef1, gr->bn1_w, gr->bn1_b, s, 4));
+  MDIL_TRY(launch_bn_bwd_apply(T3, nullptr, nullptr, sv->p, st1, coef1, T1, N, HW, C, s));
+
+  // ---- pair 1 backward: dp -> da' -> dx (+ residual dy * (y>0))
+  a.in = T1; a.wstream_tc = p4_stream(packed, 3); a.mid_mask = sv->a; a.mid_out = T2; a.out = dx;
+  a.epi = kEpiBwdResidual; a.e0 = dy; a.e1 = y; a.e_stats = nullptr; a.sums = nullptr;
+  MDIL_TRY(launch_pair(a, s));
+  MDIL_TRY(nb1d_wgrad_p4(d, false, sv->a, nullptr, nullptr, T1, gr->w13_1, gr->b13_1, wacc + 2 * WS, bacc + 2 * CP, &ul, s));
+  MDIL_TRY(nb1d_wgrad_p4(d, true, x, nullptr, nullptr, T2, gr->w31_1, gr->b31_1, wacc + 3 * WS, bacc + 3 * CP, &ul, s));
+  return launch_wgrad_unpack_p4(ul, s);
+}
+
 int mdil_nb1d_bwd(const mdil_nb1d_desc* d, const float* dy, const float* x, const float* y, const mdil_nb1d_weights* w,
                   const float* packed, const float* drop_mask, const mdil_nb1d_saved* sv, float* dx,
                   const mdil_nb1d_grads* gr, void* ws, size_t ws_bytes, void* stream) {
@@ -251,6 +386,7 @@ int mdil_nb1d_bwd(const mdil_nb1d_desc* d, const float* dy, const float* x, cons
   MDIL_REQUIRE(ws_bytes >= mdil_nb1d_bwd_workspace_bytes(d), "nb1d_bwd: workspace too small");
   MDIL_REQUIRE(sv != nullptr && sv->a && sv->p && sv->c && sv->s && sv->stats, "nb1d_bwd: saved tensors missing");
   MDIL_REQUIRE(dx != nullptr && gr != nullptr, "nb1d_bwd: dx/grads required");
+  if (p4_ok(d)) return nb1d_bwd_p4(d, dy, x, y, w, packed, drop_mask, sv, dx, gr, ws, S(stream));
   const int C = d->C, N = d->N, H = d->H, W = d->W;
   const long CC = (long)C * C;
   const size_t HW = (size_t)H * W;

@@ -117,15 +117,20 @@ int launch_bn_bwd_stats(const float* dy, const float* y, const float* drop, cons
 }
 
 // ------------------------------------------------------------------ BN finalize (forward)
+// fold > 1 (packed-4 view of the C = 16 blocks): the sums arrive per (pixel slot, channel) = [2][fold * C]; channel c
+// sums its `fold` slots, and the statistics are also written replicated per slot into stats_rep [4][fold * C]
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, int ldsum, double count, int C,
                                    const float* __restrict__ gamma, const float* __restrict__ beta, float* rm, float* rv,
-                                   float eps, float momentum, int train, float* __restrict__ stats) {
+                                   float eps, float momentum, int train, float* __restrict__ stats, int fold,
+                                   float* __restrict__ stats_rep) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float mean, var;
   if (train) {
-    double m = sums[c] / count;
-    double v = sums[ldsum + c] / count - m * m;
+    double s1 = 0.0, s2 = 0.0;
+    for (int p = 0; p < fold; ++p) { s1 += sums[p * C + c]; s2 += sums[ldsum + p * C + c]; }
+    double m = s1 / count;
+    double v = s2 / count - m * m;
     if (v < 0.0) v = 0.0;
     mean = (float)m;
     var = (float)v;
@@ -138,15 +143,39 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, int ldsum, d
   }
   float invstd = 1.0f / sqrtf(var + eps);
   float scale = gamma[c] * invstd;
+  const float shift = beta[c] - mean * scale;
   stats[c] = mean;
   stats[C + c] = invstd;
   stats[2 * C + c] = scale;
-  stats[3 * C + c] = beta[c] - mean * scale;
+  stats[3 * C + c] = shift;
+  if (stats_rep != nullptr) {
+    const int CF = fold * C;
+    for (int p = 0; p < fold; ++p) {
+      stats_rep[p * C + c] = mean;
+      stats_rep[CF + p * C + c] = invstd;
+      stats_rep[2 * CF + p * C + c] = scale;
+      stats_rep[3 * CF + p * C + c] = shift;
+    }
+  }
 }
 
 int launch_bn_finalize(const double* sums, int ldsum, double count, int C, const float* gamma, const float* beta,
-                       float* rm, float* rv, float eps, float momentum, int train, float* stats, cudaStream_t s) {
-  bn_finalize_kernel<<<cdiv(C, 128), 128, 0, s>>>(sums, ldsum, count, C, gamma, beta, rm, rv, eps, momentum, train, stats);
+                       float* rm, float* rv, float eps, float momentum, int train, float* stats, cudaStream_t s,
+                       int fold, float* stats_rep) {
+  bn_finalize_kernel<<<cdiv(C, 128), 128, 0, s>>>(sums, ldsum, count, C, gamma, beta, rm, rv, eps, momentum, train, stats,
+                                                  fold, stats_rep);
+  MDIL_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void replicate_stats_kernel(const float* __restrict__ stats, float* __restrict__ rep, int C, int fold) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 4 * fold * C) return;
+  const int k = i / (fold * C), c = i % C;
+  rep[i] = stats[k * C + c];
+}
+int launch_replicate_stats(const float* stats, float* rep, int C, int fold, cudaStream_t s) {
+  replicate_stats_kernel<<<cdiv(4 * fold * C, 128), 128, 0, s>>>(stats, rep, C, fold);
   MDIL_LAUNCH_CHECK();
   return 0;
 }
@@ -186,10 +215,11 @@ int launch_bn_act(const float* u, const float* stats, const float* drop, const f
 // ------------------------------------------------------------------ BN backward finalize / apply
 __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, double count, int C,
                                        const float* __restrict__ gamma, const float* __restrict__ stats,
-                                       float* __restrict__ coef, float* dgamma, float* dbeta) {
+                                       float* __restrict__ coef, float* dgamma, float* dbeta, int fold) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  double sdz = sums[c], sdzu = sums[C + c];
+  double sdz = 0.0, sdzu = 0.0;      // fold > 1: sums are [2][fold * C] per (pixel slot, channel)
+  for (int p = 0; p < fold; ++p) { sdz += sums[p * C + c]; sdzu += sums[fold * C + p * C + c]; }
   coef[c] = gamma[c] * stats[C + c];
   coef[C + c] = (float)(sdz / count);
   coef[2 * C + c] = (float)(sdzu / count);
@@ -198,8 +228,8 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, double c
 }
 
 int launch_bn_bwd_finalize(const double* sums, double count, int C, const float* gamma, const float* stats, float* coef,
-                           float* dgamma, float* dbeta, cudaStream_t s) {
-  bn_bwd_finalize_kernel<<<cdiv(C, 128), 128, 0, s>>>(sums, count, C, gamma, stats, coef, dgamma, dbeta);
+                           float* dgamma, float* dbeta, cudaStream_t s, int fold) {
+  bn_bwd_finalize_kernel<<<cdiv(C, 128), 128, 0, s>>>(sums, count, C, gamma, stats, coef, dgamma, dbeta, fold);
   MDIL_LAUNCH_CHECK();
   return 0;
 }

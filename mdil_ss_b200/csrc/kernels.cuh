@@ -12,9 +12,11 @@ int launch_channel_stats(const float* x, size_t P, int ld, int coff, int cnt, do
 
 // stats [4][C] = mean, invstd, scale (=gamma*invstd), shift (=beta-mean*scale).
 // train: batch statistics from sums (count pixels) and running-stat update; else running stats.
+// fold > 1: sums are [2][fold*C] per (pixel slot, channel) of a packed view and are folded over the slots (ldsum =
+// fold*C); stats_rep (nullable) [4][fold*C] receives the statistics replicated per slot.
 int launch_bn_finalize(const double* sums, int ldsum, double count, int C, const float* gamma, const float* beta,
                        float* running_mean, float* running_var, float eps, float momentum, int train, float* stats,
-                       cudaStream_t s);
+                       cudaStream_t s, int fold = 1, float* stats_rep = nullptr);
 
 // y = relu((u*scale+shift) * drop[n][c] + res)   (drop, res nullable)
 int launch_bn_act(const float* u, const float* stats, const float* drop, const float* res, float* y, int N, size_t HW,
@@ -27,7 +29,7 @@ int launch_bn_bwd_stats(const float* dy, const float* y, const float* drop, cons
 
 // coef [3][C] = gamma*invstd, sum dz / n, sum dz*uhat / n ; dgamma/dbeta nullable
 int launch_bn_bwd_finalize(const double* sums, double count, int C, const float* gamma, const float* stats, float* coef,
-                           float* dgamma, float* dbeta, cudaStream_t s);
+                           float* dgamma, float* dbeta, cudaStream_t s, int fold = 1);   // fold: sums are [2][fold*C]
 
 // du = coef0 * (dz - coef1 - uhat*coef2)
 int launch_bn_bwd_apply(const float* dy, const float* y, const float* drop, const float* u, const float* stats,
@@ -39,6 +41,8 @@ int launch_pool_fwd(const float* x, float* u, int N, int H, int W, int Cin, int 
 int launch_pool_bwd(const float* x, const float* du, float* dx, int N, int H, int W, int Cin, int ldin, int ldu,
                     int coff, int accumulate, cudaStream_t s);
 
+// rep[k][p*C + c] = stats[k][c] for k < 4, p < fold (BatchNorm statistics replicated per pixel slot of a packed view)
+int launch_replicate_stats(const float* stats, float* rep, int C, int fold, cudaStream_t s);
 int launch_scale(float* x, size_t n, const double* inv_den /*nullable: multiply by 1/(*inv_den)*/, const float* mul,
                  cudaStream_t s);
 int launch_adam(float* param, const float* grad, float* m, float* v, size_t n, float lr, float b1, float b2, float eps,
@@ -101,11 +105,21 @@ struct PairArgs {
   double* sums;            // nullable: [2][C] (fwd: sum out, sum out^2; epi1: sum out, sum out*phat)
   int N, H, W, C, dil, has_adapter, vert_first;
   int trace;               // debug: CTA 0 prints its phase timestamps (MDIL_TC_TRACE=1)
+  int view_c;              // 0, or the logical channel count when the launch runs on a packed view (profiling kinds only)
 };
 int launch_pair(const PairArgs& a, cudaStream_t s);          // dispatch: tensor-core kernel when wstream_tc != NULL
 int launch_pair_ffma(const PairArgs& a, cudaStream_t s);     // nb1d_pair.cu (FP32 FFMA; all C)
 int launch_pair_h3(const PairArgs& a, cudaStream_t s);       // nb1d_pair_h3.cu (tcgen05 kind::f16, fp16/bf16 split operands; default)
 int launch_pack_block_h3(const float* const* w6, void* packed, int C, int has_adapter, cudaStream_t s);
+// packed-4 view of a C = 16 block without adapter ([N,H,W,16] read as [N,H,W/4,64]: four pixels of a row form one
+// 64-"channel" row): the 16-bit hi/lo images of the equivalent 64 x 64 tap matrices (block-diagonal for the 3x1 convs,
+// block-banded over the three GROUP taps for the 1x3 convs) + the four conv biases replicated per pixel slot (float [4][64])
+int launch_pack_block_p4(const float* const* w4, const float* const* b4, void* packed16, float* bias_rep, cudaStream_t s);
+// weight / bias gradients of the packed-4 view: acc [3][64][64] (tap, ci', co') of wgrad_tc<64> -> dW [16][16][3] (torch
+// layout [co][ci][k]), dbacc [64] -> db [16].  horizontal: the conv runs along the packing axis (1x3).
+struct UnpackP4Item { const float* acc; float* dW; const float* dbacc; float* db; int horizontal; };
+struct UnpackP4List { int n; UnpackP4Item item[4]; };
+int launch_wgrad_unpack_p4(const UnpackP4List& ul, cudaStream_t s);
 int launch_pair_tc3(const PairArgs& a, cudaStream_t s);      // nb1d_pair_tc3.cu (persistent pipelined 3xTF32 tcgen05 kernel; A/B)
 int launch_pack_tc3(const float* src_stream, float* dst_stream, int C, int has_adapter, cudaStream_t s);
 // one launch: fp32 FFMA streams (write_fp32) and/or 3xTF32 tensor-core images (tc_order 0 = none, 3) of a whole block

@@ -959,6 +959,53 @@ __global__ void pack_block_h3_kernel(const PackSrc src, unsigned short* __restri
   }
 }
 
+// ---- packed-4 view of a C = 16 block (no adapter, dilation 1): four pixels of a row form one 64-"channel" operand row,
+// so the block runs on the C = 64 tensor-core kernel (the FFMA kernel it replaces ran at 0.09 of the HBM roof).  The 16x16
+// tap matrices become 64x64 ones: block-diagonal for the 3x1 convs (taps along H), block-banded across the three GROUP
+// taps for the 1x3 convs (taps along W, the packing axis): group tap gt connects input slot pi to output slot po when
+// 4 (gt - 1) + pi - po + 1 is a conv tap (0..2).  Same stream / chunk order as pack_block_h3_kernel without adapter.
+struct PackSrcP4 { const float* w[4]; const float* b[4]; };   // w31_1, w13_1, w31_2, w13_2 ([co][ci][3]) and their biases
+__global__ void pack_block_p4_kernel(const PackSrcP4 src, unsigned short* __restrict__ packed, float* __restrict__ bias_rep,
+                                     int fmt_override) {
+  constexpr int C = 64, CW = 16, CC = C * C, nkc = C / KCH;
+  const long total = 4L * 6 * CC;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int which = (int)(i / (6 * CC));
+    const int r = (int)(i % (6 * CC));
+    const int slab = r / CC, aa = (r % CC) / C, bb = r % C;
+    const bool bwd = which >= 2;
+    const int pairsel = (which == 0 || which == 3) ? 0 : 1;
+    const int conv = slab / 3, tap = slab % 3;
+    const int is13 = bwd ? (conv == 0) : (conv == 1);
+    const float* w = src.w[pairsel * 2 + is13];
+    const int pi = aa >> 4, ca = aa & 15, po = bb >> 4, cb = bb & 15;
+    int teff = tap;                       // effective conv-window position of this (group tap, slot pair)
+    bool nz = true;
+    if (is13) { teff = 4 * (tap - 1) + pi - po + 1; nz = teff >= 0 && teff <= 2; }
+    else nz = pi == po;
+    float v = 0.f;
+    if (nz) v = bwd ? __ldg(w + (ca * CW + cb) * 3 + (2 - teff)) : __ldg(w + (cb * CW + ca) * 3 + teff);
+    const int j = aa / KCH, kk = aa % KCH, nrow = bb;
+    const int g = slab < 3 ? j * 3 + slab : nkc * 3 + j * 3 + (slab - 3);
+    const int fmt = fmt_override >= 0 ? fmt_override : (bwd ? 1 : 0);
+    unsigned short hi, lo;
+    if (fmt == 0) {
+      const __half h = __float2half_rn(v);
+      const __half l = __float2half_rn(v - __half2float(h));
+      hi = __half_as_ushort(h); lo = __half_as_ushort(l);
+    } else {
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+      hi = __bfloat16_as_ushort(h); lo = __bfloat16_as_ushort(l);
+    }
+    const int off = nrow * 32 + ((((kk >> 3) ^ ((nrow >> 1) & 3)) << 3) | (kk & 7));
+    unsigned short* stage = packed + (long)which * 14 * CC + (long)g * 2 * C * KCH;
+    stage[off] = hi;
+    stage[C * KCH + off] = lo;
+    if (i < 4 * C) bias_rep[i] = src.b[i / C] != nullptr ? __ldg(src.b[i / C] + (i & 15)) : 0.f;
+  }
+}
+
 }  // namespace h3
 
 static int h3_fmt_override() {
@@ -978,6 +1025,16 @@ int launch_pack_block_h3(const float* const* w6, void* packed, int C, int has_ad
   int grid = (int)((total + 255) / 256);
   if (grid > kNumSMs * 4) grid = kNumSMs * 4;
   h3::pack_block_h3_kernel<<<grid, 256, 0, s>>>(src, reinterpret_cast<unsigned short*>(packed), C, has_adapter, h3_fmt_override());
+  MDIL_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_pack_block_p4(const float* const* w4, const float* const* b4, void* packed16, float* bias_rep, cudaStream_t s) {
+  h3::PackSrcP4 src;
+  for (int i = 0; i < 4; ++i) { src.w[i] = w4[i]; src.b[i] = b4[i]; }
+  const long total = 4L * 6 * 64 * 64;
+  h3::pack_block_p4_kernel<<<(int)((total + 255) / 256), 256, 0, s>>>(src, reinterpret_cast<unsigned short*>(packed16), bias_rep,
+                                                                     h3_fmt_override());
   MDIL_LAUNCH_CHECK();
   return 0;
 }

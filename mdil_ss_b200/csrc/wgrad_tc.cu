@@ -447,6 +447,30 @@ __global__ void wgrad_unpack_multi_kernel(const UnpackList ul, int C) {
     for (int c = threadIdx.x; c < C; c += blockDim.x) it.db[c] = it.dbacc[c];
 }
 
+// packed-4 view (a C = 16 block run as C = 64 on [N,H,W/4,64]): fold the [3][64][64] accumulators of wgrad_tc<64> back
+// to the 16 x 16 x 3 weight gradient (torch layout [co][ci][k]) and the [64] bias sums to [16]
+__global__ void wgrad_unpack_p4_kernel(const UnpackP4List ul) {
+  const UnpackP4Item& it = ul.item[blockIdx.x];
+  for (int i = threadIdx.x; i < 16 * 16 * 3; i += blockDim.x) {
+    const int k = i % 3, ci = (i / 3) % 16, co = i / 48;
+    float sum = 0.f;
+    if (it.horizontal) {
+      for (int gt = 0; gt < 3; ++gt)
+        for (int pi = 0; pi < 4; ++pi) {
+          const int po = 4 * (gt - 1) + pi + 1 - k;          // 4 (gt - 1) + pi - po + 1 == k
+          if (po >= 0 && po < 4) sum += it.acc[(gt * 64 + pi * 16 + ci) * 64 + po * 16 + co];
+        }
+    } else {
+      for (int p = 0; p < 4; ++p) sum += it.acc[(k * 64 + p * 16 + ci) * 64 + p * 16 + co];
+    }
+    it.dW[(co * 16 + ci) * 3 + k] = sum;
+  }
+  if (it.db != nullptr && threadIdx.x < 16) {
+    const int c = threadIdx.x;
+    it.db[c] = (it.dbacc[c] + it.dbacc[16 + c]) + (it.dbacc[32 + c] + it.dbacc[48 + c]);
+  }
+}
+
 template <int C>
 int launch_c(const WgradTcArgs& a, cudaStream_t s) {
   using K = Cfg<C>;
@@ -505,6 +529,13 @@ int launch_wgrad_unpack_multi(const UnpackList& ul, int C, cudaStream_t s) {
   int grid = (int)((total + 255) / 256);
   if (grid > kNumSMs) grid = kNumSMs;
   wtc::wgrad_unpack_multi_kernel<<<dim3((unsigned)grid, (unsigned)ul.n), 256, 0, s>>>(ul, C);
+  MDIL_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_wgrad_unpack_p4(const UnpackP4List& ul, cudaStream_t s) {
+  if (ul.n == 0) return 0;
+  wtc::wgrad_unpack_p4_kernel<<<ul.n, 256, 0, s>>>(ul);
   MDIL_LAUNCH_CHECK();
   return 0;
 }

@@ -58,7 +58,7 @@ def grad_target(param: torch.Tensor, need: bool):
     by two forwards, as in steps 2/3) goes through a temporary that autograd adds as usual."""
     if not need:
         return None, None
-    g = param.grad
+    g = param.grad if param.is_leaf else None      # nn.DataParallel replicas hold non-leaf views of the parameters
     if getattr(param, "_mdil_grad_fresh", False) and g is not None and g.is_contiguous() and g.shape == param.shape \
             and g.device == param.device:
         param._mdil_grad_fresh = False

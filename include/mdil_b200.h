@@ -180,6 +180,18 @@ int mdil_scale_by_device_scalar(float* x, size_t n, const float* grad_out, void*
 int mdil_argmax_confusion(const float* logits, const int64_t* labels, int N, int C, int H, int W, int64_t* pred,
                           long long* conf, void* stream);
 
+/* ----------------------------------------------- input co-transform (next row) */
+/* MyCoTransform.__call__ (train_new_task_step2.py:48-81) + ToTensor / ToLabel / Relabel(255, C-1) (transform.py:63-79)
+ * for a batch of uint8 source images [N,Hs,Ws,3] and labels [N,Hs,Ws]: Pillow's BILINEAR (image) / NEAREST (label)
+ * resize to H x W, optional horizontal flip, translation by (tx, ty) in -2..2 with the reference's fill rules.
+ * xtab [W][2+KX] / ytab [H][2+KY]: per output column / row the first source index, the tap count and Pillow's 22-bit
+ * coefficients; xnear [W] / ynear [H]: source index of the NEAREST resize; params [N][3] = hflip, tx, ty or NULL (no
+ * augmentation).  All tables are device int32 arrays built by the host (mdil_ss_b200/cotransform.py).
+ * out_img float [N,3,H,W] in [0,1], out_lab int64 [N,1,H,W].  Bit-exact with the reference. */
+int mdil_cotransform(const unsigned char* img, const unsigned char* lab, int N, int Hs, int Ws, int H, int W, const int* xtab,
+                     int KX, const int* ytab, int KY, const int* xnear, const int* ynear, const int* params, int num_classes,
+                     float* out_img, int64_t* out_lab, void* stream);
+
 /* ------------------------------------------------------- optimiser (next row) */
 /* Adam as the drivers configure it (train_new_task_step2.py:237-239): L2 weight decay
  * folded into the gradient, bias correction.  Flat multi-tensor form over n floats. */

@@ -683,6 +683,13 @@ int mdil_argmax_confusion(const float* logits, const int64_t* labels, int N, int
   return launch_argmax_confusion(logits, labels, N, C, H, W, pred, conf, S(stream));
 }
 
+int mdil_cotransform(const unsigned char* img, const unsigned char* lab, int N, int Hs, int Ws, int H, int W, const int* xtab,
+                     int KX, const int* ytab, int KY, const int* xnear, const int* ynear, const int* params, int num_classes,
+                     float* out_img, int64_t* out_lab, void* stream) {
+  return launch_cotransform(img, lab, N, Hs, Ws, H, W, xtab, KX, ytab, KY, xnear, ynear, params, num_classes, out_img,
+                            reinterpret_cast<long long*>(out_lab), S(stream));
+}
+
 int mdil_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1,
                    float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream) {
   return launch_adam(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, S(stream));

@@ -160,4 +160,9 @@ int launch_kd(const float* student, const float* teacher, int N, int C, int H, i
 int launch_argmax_confusion(const float* logits, const int64_t* labels, int N, int C, int H, int W, int64_t* pred,
                             long long* conf, cudaStream_t s);
 
+// ---------------------------------------------------------------- cotransform.cu
+int launch_cotransform(const unsigned char* img, const unsigned char* lab, int N, int Hs, int Ws, int H, int W, const int* xtab,
+                       int KX, const int* ytab, int KY, const int* xnear, const int* ynear, const int* params, int num_classes,
+                       float* out_img, long long* out_lab, cudaStream_t s);
+
 }  // namespace mdil

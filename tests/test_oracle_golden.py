@@ -207,3 +207,43 @@ def test_multitask_iteration_against_torch_adam():
             assert off <= max(2, da.numel() // 50), f"{n}: {off} of {da.numel()} entries moved differently"
     print("worst fraction of entries moving differently:", worst)
     assert 0 < moved <= len(names)
+
+
+# ------------------------------------------------------------------------------ co-transform
+def test_cotransform_oracle_matches_reference_fixture():
+    """oracle/cotransform_oracle.py against the outputs of the reference's own MyCoTransform (Pillow + torchvision;
+    tests/golden/make_golden_cotransform.py): bit-exact images and labels for down-, up- and non-integer rescaling, both
+    flip states, positive and negative translations, and the no-augmentation (validation) call."""
+    from oracle import cotransform_oracle as co
+    g = golden("cotransform.npz")
+    for i in range(int(g["n"])):
+        hf, tx, ty, h, w, ncls = (int(v) for v in g[f"par{i}"])
+        x, y = co.cotransform(g[f"img{i}"], g[f"lab{i}"], h, w, ncls, True, bool(hf), tx, ty)
+        assert np.array_equal(x, g[f"x{i}"]), f"case {i}: image"
+        assert np.array_equal(y, g[f"y{i}"]), f"case {i}: label"
+    x, y = co.cotransform(g["img0"], g["lab0"], 48, 96, 20, False)
+    assert np.array_equal(x, g["x_noaug"]) and np.array_equal(y, g["y_noaug"])
+
+
+def test_cotransform_host_tables_match_oracle():
+    """The coefficient / index tables the product's host side hands to the kernel equal the oracle's restatement of
+    Pillow's (sizes of the three datasets to the training crop, plus odd cases)."""
+    from mdil_ss_b200 import cotransform as prod
+    from oracle import cotransform_oracle as co
+    for in_size, out_size in ((2048, 1024), (1024, 512), (1280, 1024), (720, 512), (1920, 1024), (1080, 512), (54, 64), (64, 64), (97, 31)):
+        tab, k = prod._bilinear_table(in_size, out_size)
+        xmin, cnt, kk = co.bilinear_coeffs(in_size, out_size)
+        assert k == kk.shape[1]
+        assert np.array_equal(tab[:, 0], xmin) and np.array_equal(tab[:, 1], cnt) and np.array_equal(tab[:, 2:], kk)
+        assert np.array_equal(prod._nearest_table(in_size, out_size), co.nearest_index(in_size, out_size))
+
+
+def test_cotransform_draws_follow_the_reference_order():
+    import random
+    from mdil_ss_b200.cotransform import GpuCoTransform
+    g = golden("cotransform.npz")
+    seeds = [1, 2, 3, 4, 5, 6, 7, 9]          # tests/golden/make_golden_cotransform.py CASES
+    for i, seed in enumerate(seeds):
+        random.seed(seed)
+        p = GpuCoTransform.draw_params(1)[0]
+        assert [int(v) for v in p] == [int(v) for v in g[f"par{i}"][:3]]

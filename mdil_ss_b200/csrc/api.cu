@@ -170,8 +170,8 @@ static bool p4_ok(const mdil_nb1d_desc* d) {
 }
 
 size_t mdil_nb1d_fwd_workspace_bytes(const mdil_nb1d_desc* d) {
-  const int Cs = d->C == 16 ? 64 : d->C;     // packed-4 view: sums per (pixel slot, channel)
-  return 256 + (size_t)4 * Cs * sizeof(double) + (size_t)4 * Cs * sizeof(float) + 512;
+  const int Cs = d->C == 16 ? 64 : d->C;     // packed-4 view: sums per (pixel slot, channel), two replicated statistics sets
+  return 256 + (size_t)4 * Cs * sizeof(double) + (size_t)8 * Cs * sizeof(float) + 1024;
 }
 
 size_t mdil_nb1d_bwd_workspace_bytes(const mdil_nb1d_desc* d) {
@@ -227,6 +227,20 @@ static int nb1d_fwd_p4(const mdil_nb1d_desc* d, const float* x, const mdil_nb1d_
   a.N = d->N; a.H = d->H; a.W = d->W / 4; a.C = CP; a.has_adapter = 0; a.vert_first = 1; a.epi = kEpiFwd; a.dil = 1; a.view_c = C;
   a.in = x; a.wstream_tc = p4_stream(packed, 0); a.b1 = p4_bias(packed, 0); a.b2 = p4_bias(packed, 1);
   a.mid_out = d->save ? sv->a : nullptr; a.out = sv->p; a.sums = d->train ? sums1 : nullptr;
+  if (!d->train) {
+    // eval mode: both BatchNorms use running statistics, known before the block runs: pair 1, then pair 2 whose epilogue
+    // applies BN2 + residual + ReLU (no s tensor, no separate elementwise pass)
+    float* rep2 = cv.take<float>(4 * CP);
+    MDIL_TRY(launch_bn_finalize(sums1, CP, count, C, w->bn1.weight, w->bn1.bias, w->bn1.running_mean, w->bn1.running_var,
+                                d->eps, d->momentum, 0, st1, s, 4, rep1));
+    MDIL_TRY(launch_bn_finalize(sums2, CP, count, C, w->bn2.weight, w->bn2.bias, w->bn2.running_mean, w->bn2.running_var,
+                                d->eps, d->momentum, 0, st2, s, 4, rep2));
+    MDIL_TRY(launch_pair(a, s));
+    a.in = sv->p; a.in_scale = rep1 + 2 * CP; a.in_shift = rep1 + 3 * CP; a.wstream_tc = p4_stream(packed, 1);
+    a.b1 = p4_bias(packed, 2); a.b2 = p4_bias(packed, 3);
+    a.mid_out = nullptr; a.out = y; a.sums = nullptr; a.epi = kEpiFwdBnRes; a.e0 = x; a.e_stats = rep2;
+    return launch_pair(a, s);
+  }
   MDIL_TRY(launch_pair(a, s));
   MDIL_TRY(launch_bn_finalize(sums1, CP, count, C, w->bn1.weight, w->bn1.bias, w->bn1.running_mean, w->bn1.running_var,
                               d->eps, d->momentum, d->train, st1, s, 4, rep1));
@@ -262,6 +276,20 @@ int mdil_nb1d_fwd(const mdil_nb1d_desc* d, const float* x, const mdil_nb1d_weigh
   // pair 1: x -> a -> p
   a.in = x; a.wstream = packed; a.wstream_tc = tc_stream(packed, C, 0); a.b1 = w->b31_1; a.b2 = w->b13_1; a.bad = d->has_adapter ? w->bp1 : nullptr;
   a.mid_out = d->save ? sv->a : nullptr; a.out = sv->p; a.sums = d->train ? sums1 : nullptr; a.dil = 1;
+  if (!d->train && use_tensor_cores(C) && pair_impl_mode() == 4) {
+    // eval mode (teacher forward of steps 2/3, validation: train_new_task_step2.py:291,398-438): both BatchNorms use
+    // running statistics, known before the block runs: pair 1, then pair 2 whose epilogue applies BN2 + residual + ReLU
+    // -- two fused launches and 5 tensor passes (R x, W p | R p, R x, W y) instead of five launches and 7
+    MDIL_TRY(launch_bn_finalize(sums1, C, count, C, w->bn1.weight, w->bn1.bias, w->bn1.running_mean, w->bn1.running_var,
+                                d->eps, d->momentum, 0, st1, s));
+    MDIL_TRY(launch_bn_finalize(sums2, C, count, C, w->bn2.weight, w->bn2.bias, w->bn2.running_mean, w->bn2.running_var,
+                                d->eps, d->momentum, 0, st2, s));
+    MDIL_TRY(launch_pair(a, s));
+    a.in = sv->p; a.in_scale = st1 + 2 * C; a.in_shift = st1 + 3 * C; a.wstream = packed + 7 * CC; a.wstream_tc = tc_stream(packed, C, 1);
+    a.b1 = w->b31_2; a.b2 = w->b13_2; a.bad = d->has_adapter ? w->bp2 : nullptr;
+    a.mid_out = nullptr; a.out = y; a.sums = nullptr; a.dil = d->dil; a.epi = kEpiFwdBnRes; a.e0 = x; a.e_stats = st2;
+    return launch_pair(a, s);
+  }
   MDIL_TRY(launch_pair(a, s));
   MDIL_TRY(launch_bn_finalize(sums1, C, count, C, w->bn1.weight, w->bn1.bias, w->bn1.running_mean, w->bn1.running_var,
                               d->eps, d->momentum, d->train, st1, s));

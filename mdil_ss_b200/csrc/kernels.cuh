@@ -84,7 +84,9 @@ int launch_pack(const float* src, float* dst, int T, int A, int Apad, int B, int
                 cudaStream_t s);
 
 // ---------------------------------------------------------------- nb1d_pair.cu
-enum PairEpilogue { kEpiFwd = 0, kEpiBwdMaskStats = 1, kEpiBwdResidual = 2 };
+// kEpiFwdBnRes (eval-mode forward of pair 2, tensor-core kernel only): out = relu((acc + b) * scale + shift + e0) with
+// e_stats = the running-statistics BatchNorm [4][C] and e0 = the block input: BN2 + residual + ReLU without another pass
+enum PairEpilogue { kEpiFwd = 0, kEpiBwdMaskStats = 1, kEpiBwdResidual = 2, kEpiFwdBnRes = 3 };
 
 struct PairArgs {
   const float* in;         // [N,H,W,C]
@@ -99,9 +101,9 @@ struct PairArgs {
   float* mid_out;          // nullable: store mid (a / c / dc' / da')
   float* out;
   int epi;
-  const float* e0;         // epi1: p            epi2: dy
+  const float* e0;         // epi1: p            epi2: dy            epi3: block input x (residual)
   const float* e1;         // epi2: y
-  const float* e_stats;    // epi1: [4][C] mean, invstd, scale, shift of BN1
+  const float* e_stats;    // epi1: [4][C] mean, invstd, scale, shift of BN1;  epi3: the same of BN2 (running statistics)
   double* sums;            // nullable: [2][C] (fwd: sum out, sum out^2; epi1: sum out, sum out*phat)
   int N, H, W, C, dil, has_adapter, vert_first;
   int trace;               // debug: CTA 0 prints its phase timestamps (MDIL_TC_TRACE=1)

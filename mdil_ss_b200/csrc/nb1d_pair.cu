@@ -69,7 +69,7 @@ void pair_profile_record_begin(const PairArgs& a, cudaStream_t s, void** out) {
   prof::Rec* rec = new prof::Rec{nullptr, nullptr, -1};
   const int lc = a.view_c != 0 ? a.view_c : a.C;     // logical channel count (packed-4 launches report as C = 16)
   const int ci = lc == 16 ? 0 : (lc == 64 ? 1 : 2);
-  const int ph = a.epi == kEpiFwd ? (a.in_scale == nullptr ? 0 : 1) : (a.epi == kEpiBwdMaskStats ? 2 : 3);
+  const int ph = (a.epi == kEpiFwd || a.epi == kEpiFwdBnRes) ? (a.in_scale == nullptr ? 0 : 1) : (a.epi == kEpiBwdMaskStats ? 2 : 3);
   rec->kind = ci * 4 + ph;
   if (cudaEventCreate(&rec->a) != cudaSuccess || cudaEventCreate(&rec->b) != cudaSuccess) { delete rec; return; }
   cudaEventRecord(rec->a, s);

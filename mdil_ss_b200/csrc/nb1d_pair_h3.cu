@@ -728,6 +728,16 @@ pair_h3_kernel(const __grid_constant__ PairArgs a, const __grid_constant__ Geo g
         } else if (a.epi == kEpiBwdResidual) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) x[i] += ev[i];
+        } else if (a.epi == kEpiFwdBnRes) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            const float4 scl = __ldg(reinterpret_cast<const float4*>(a.e_stats + 2 * C + ch0 + i));
+            const float4 sft = __ldg(reinterpret_cast<const float4*>(a.e_stats + 3 * C + ch0 + i));
+            x[i] = fmaxf(fmaf(x[i], scl.x, sft.x) + ev[i], 0.f);
+            x[i + 1] = fmaxf(fmaf(x[i + 1], scl.y, sft.y) + ev[i + 1], 0.f);
+            x[i + 2] = fmaxf(fmaf(x[i + 2], scl.z, sft.z) + ev[i + 2], 0.f);
+            x[i + 3] = fmaxf(fmaf(x[i + 3], scl.w, sft.w) + ev[i + 3], 0.f);
+          }
         } else {
 #pragma unroll
           for (int i = 0; i < 16; ++i) s2v[i] = x[i] * x[i];
@@ -1041,7 +1051,7 @@ int launch_pack_block_p4(const float* const* w4, const float* const* b4, void* p
 
 int launch_pair_h3(const PairArgs& a, cudaStream_t s) {
   const int ov = h3_fmt_override();
-  const int fmt = ov >= 0 ? ov : (a.epi == kEpiFwd ? 0 : 1);
+  const int fmt = ov >= 0 ? ov : ((a.epi == kEpiFwd || a.epi == kEpiFwdBnRes) ? 0 : 1);   // forward: fp16 halves, backward: bf16
   if (a.trace) {
     if (a.C == 128) return fmt == 0 ? h3::launch_c<128, 0, true>(a, s) : h3::launch_c<128, 1, true>(a, s);
     if (a.C == 64) return fmt == 0 ? h3::launch_c<64, 0, true>(a, s) : h3::launch_c<64, 1, true>(a, s);

@@ -308,9 +308,16 @@ int mdil_nb1d_fwd(const mdil_nb1d_desc* d, const float* x, const mdil_nb1d_weigh
 // One weight gradient of the block: tensor-core path (C = 64, 128) or the generic FFMA tap kernel.
 // taps: 3 (vertical when vert != 0, else horizontal, dilation d) or 1 (1x1 adapter).
 // (tensor-core path: `acc_scratch` = this gradient's own zeroed [taps][C][C] slot; its unpack is deferred to `ul`)
+struct WgradJobList { int n; WgradTcArgs job[3]; };   // tensor-core weight gradients waiting for their shared launch
+static int flush_wgrad_jobs(WgradJobList* jl, cudaStream_t s) {
+  const int n = jl->n;
+  jl->n = 0;
+  return launch_wgrad_tc_multi(jl->job, n, s);
+}
+
 static int nb1d_wgrad(const mdil_nb1d_desc* d, int dil, bool vert, int taps, const float* A, const float* sc,
                       const float* sh, const float* G, float* dW, float* db, float* acc_scratch, float* db_scratch,
-                      UnpackList* ul, cudaStream_t s) {
+                      UnpackList* ul, WgradJobList* jl, cudaStream_t s) {
   const int C = d->C;
   if (dW == nullptr) {
     MDIL_REQUIRE(db == nullptr, "nb1d_bwd: bias gradient without weight gradient is not supported");
@@ -323,7 +330,7 @@ static int nb1d_wgrad(const mdil_nb1d_desc* d, int dil, bool vert, int taps, con
     memset(&w, 0, sizeof(w));
     w.A = A; w.a_scale = sc; w.a_shift = sh; w.G = G; w.dWacc = acc_scratch; w.db = db != nullptr ? db_scratch : nullptr;
     w.N = d->N; w.H = d->H; w.W = d->W; w.C = C; w.dil = dil; w.ntaps = taps; w.vert = vert ? 1 : 0;
-    MDIL_TRY(launch_wgrad_tc(w, s));
+    jl->job[jl->n++] = w;        // launched together with the pair's other weight gradients (flush_wgrad_jobs)
     UnpackItem& it = ul->item[ul->n++];
     it.acc = acc_scratch; it.dW = dW; it.ntaps = taps; it.s_ci = s_ci; it.s_co = s_co; it.s_t = s_t;
     it.dbacc = db_scratch; it.db = db;
@@ -336,7 +343,7 @@ static int nb1d_wgrad(const mdil_nb1d_desc* d, int dil, bool vert, int taps, con
 
 // one weight gradient of the packed-4 view through wgrad_tc<64>; its [3][64][64] accumulator is folded back by `ul`
 static int nb1d_wgrad_p4(const mdil_nb1d_desc* d, bool vert, const float* A, const float* sc, const float* sh, const float* G,
-                         float* dW, float* db, float* acc, float* bacc, UnpackP4List* ul, cudaStream_t s) {
+                         float* dW, float* db, float* acc, float* bacc, UnpackP4List* ul, WgradJobList* jl) {
   if (dW == nullptr) {
     MDIL_REQUIRE(db == nullptr, "nb1d_bwd: bias gradient without weight gradient is not supported");
     return 0;
@@ -345,7 +352,7 @@ static int nb1d_wgrad_p4(const mdil_nb1d_desc* d, bool vert, const float* A, con
   memset(&w, 0, sizeof(w));
   w.A = A; w.a_scale = sc; w.a_shift = sh; w.G = G; w.dWacc = acc; w.db = db != nullptr ? bacc : nullptr;
   w.N = d->N; w.H = d->H; w.W = d->W / 4; w.C = 64; w.dil = 1; w.ntaps = 3; w.vert = vert ? 1 : 0;
-  MDIL_TRY(launch_wgrad_tc(w, s));
+  jl->job[jl->n++] = w;
   UnpackP4Item& it = ul->item[ul->n++];
   it.acc = acc; it.dW = dW; it.dbacc = bacc; it.db = db; it.horizontal = vert ? 0 : 1;
   return 0;
@@ -390,8 +397,11 @@ static int nb1d_bwd_p4(const mdil_nb1d_desc* d, const float* dy, const float* x,
   a.in = T1; a.wstream_tc = p4_stream(packed, 2); a.mid_mask = sv->c; a.mid_out = T2; a.out = T3;
   a.epi = kEpiBwdMaskStats; a.e0 = sv->p; a.e_stats = rep1; a.sums = sums1;
   MDIL_TRY(launch_pair(a, s));
-  MDIL_TRY(nb1d_wgrad_p4(d, false, sv->c, nullptr, nullptr, T1, gr->w13_2, gr->b13_2, wacc + 0 * WS, bacc + 0 * CP, &ul, s));
-  MDIL_TRY(nb1d_wgrad_p4(d, true, sv->p, rep1 + 2 * CP, rep1 + 3 * CP, T2, gr->w31_2, gr->b31_2, wacc + 1 * WS, bacc + 1 * CP, &ul, s));
+  WgradJobList jl;
+  jl.n = 0;
+  MDIL_TRY(nb1d_wgrad_p4(d, false, sv->c, nullptr, nullptr, T1, gr->w13_2, gr->b13_2, wacc + 0 * WS, bacc + 0 * CP, &ul, &jl));
+  MDIL_TRY(nb1d_wgrad_p4(d, true, sv->p, rep1 + 2 * CP, rep1 + 3 * CP, T2, gr->w31_2, gr->b31_2, wacc + 1 * WS, bacc + 1 * CP, &ul, &jl));
+  MDIL_TRY(flush_wgrad_jobs(&jl, s));
 
   // ---- BN1 backward: dq -> dp (overwrites ds)
   MDIL_TRY(launch_bn_bwd_finalize(sums1, count, C, w->bn1.weight, st1, coef1, gr->bn1_w, gr->bn1_b, s, 4));
@@ -401,8 +411,9 @@ static int nb1d_bwd_p4(const mdil_nb1d_desc* d, const float* dy, const float* x,
   a.in = T1; a.wstream_tc = p4_stream(packed, 3); a.mid_mask = sv->a; a.mid_out = T2; a.out = dx;
   a.epi = kEpiBwdResidual; a.e0 = dy; a.e1 = y; a.e_stats = nullptr; a.sums = nullptr;
   MDIL_TRY(launch_pair(a, s));
-  MDIL_TRY(nb1d_wgrad_p4(d, false, sv->a, nullptr, nullptr, T1, gr->w13_1, gr->b13_1, wacc + 2 * WS, bacc + 2 * CP, &ul, s));
-  MDIL_TRY(nb1d_wgrad_p4(d, true, x, nullptr, nullptr, T2, gr->w31_1, gr->b31_1, wacc + 3 * WS, bacc + 3 * CP, &ul, s));
+  MDIL_TRY(nb1d_wgrad_p4(d, false, sv->a, nullptr, nullptr, T1, gr->w13_1, gr->b13_1, wacc + 2 * WS, bacc + 2 * CP, &ul, &jl));
+  MDIL_TRY(nb1d_wgrad_p4(d, true, x, nullptr, nullptr, T2, gr->w31_1, gr->b31_1, wacc + 3 * WS, bacc + 3 * CP, &ul, &jl));
+  MDIL_TRY(flush_wgrad_jobs(&jl, s));
   return launch_wgrad_unpack_p4(ul, s);
 }
 
@@ -456,10 +467,13 @@ int mdil_nb1d_bwd(const mdil_nb1d_desc* d, const float* dy, const float* x, cons
   if (stop == 2) return 0;
 
   // ---- weight gradients of pair 2
-  MDIL_TRY(nb1d_wgrad(d, d->dil, false, 3, sv->c, nullptr, nullptr, T1, gr->w13_2, gr->b13_2, wacc + 0 * WS, bacc + 0 * C, &ul, s));
+  WgradJobList jl;
+  jl.n = 0;
+  MDIL_TRY(nb1d_wgrad(d, d->dil, false, 3, sv->c, nullptr, nullptr, T1, gr->w13_2, gr->b13_2, wacc + 0 * WS, bacc + 0 * C, &ul, &jl, s));
   if (d->has_adapter)
-    MDIL_TRY(nb1d_wgrad(d, 1, true, 1, sv->p, st1 + 2 * C, st1 + 3 * C, T1, gr->wp2, gr->bp2, wacc + 1 * WS, bacc + 1 * C, &ul, s));
-  MDIL_TRY(nb1d_wgrad(d, d->dil, true, 3, sv->p, st1 + 2 * C, st1 + 3 * C, T2, gr->w31_2, gr->b31_2, wacc + 2 * WS, bacc + 2 * C, &ul, s));
+    MDIL_TRY(nb1d_wgrad(d, 1, true, 1, sv->p, st1 + 2 * C, st1 + 3 * C, T1, gr->wp2, gr->bp2, wacc + 1 * WS, bacc + 1 * C, &ul, &jl, s));
+  MDIL_TRY(nb1d_wgrad(d, d->dil, true, 3, sv->p, st1 + 2 * C, st1 + 3 * C, T2, gr->w31_2, gr->b31_2, wacc + 2 * WS, bacc + 2 * C, &ul, &jl, s));
+  MDIL_TRY(flush_wgrad_jobs(&jl, s));     // the pair's three weight gradients: one launch (T1 is overwritten below)
 
   if (stop == 3) return 0;
   // ---- BN1 backward: dq -> dp (overwrites ds)
@@ -472,9 +486,10 @@ int mdil_nb1d_bwd(const mdil_nb1d_desc* d, const float* dy, const float* x, cons
   MDIL_TRY(launch_pair(a, s));
 
   // ---- weight gradients of pair 1
-  MDIL_TRY(nb1d_wgrad(d, 1, false, 3, sv->a, nullptr, nullptr, T1, gr->w13_1, gr->b13_1, wacc + 3 * WS, bacc + 3 * C, &ul, s));
-  if (d->has_adapter) MDIL_TRY(nb1d_wgrad(d, 1, true, 1, x, nullptr, nullptr, T1, gr->wp1, gr->bp1, wacc + 4 * WS, bacc + 4 * C, &ul, s));
-  MDIL_TRY(nb1d_wgrad(d, 1, true, 3, x, nullptr, nullptr, T2, gr->w31_1, gr->b31_1, wacc + 5 * WS, bacc + 5 * C, &ul, s));
+  MDIL_TRY(nb1d_wgrad(d, 1, false, 3, sv->a, nullptr, nullptr, T1, gr->w13_1, gr->b13_1, wacc + 3 * WS, bacc + 3 * C, &ul, &jl, s));
+  if (d->has_adapter) MDIL_TRY(nb1d_wgrad(d, 1, true, 1, x, nullptr, nullptr, T1, gr->wp1, gr->bp1, wacc + 4 * WS, bacc + 4 * C, &ul, &jl, s));
+  MDIL_TRY(nb1d_wgrad(d, 1, true, 3, x, nullptr, nullptr, T2, gr->w31_1, gr->b31_1, wacc + 5 * WS, bacc + 5 * C, &ul, &jl, s));
+  MDIL_TRY(flush_wgrad_jobs(&jl, s));
   return launch_wgrad_unpack_multi(ul, C, s);
 }
 

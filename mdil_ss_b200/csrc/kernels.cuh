@@ -145,6 +145,8 @@ struct WgradTcArgs {
   int trace;               // debug: CTA 0 prints its wait counters (MDIL_TC_TRACE=1)
 };
 int launch_wgrad_tc(const WgradTcArgs& a, cudaStream_t s);
+// up to three independent jobs (same C) in ONE launch, CTAs split between them: one accumulator flush per CTA instead of three
+int launch_wgrad_tc_multi(const WgradTcArgs* a, int n, cudaStream_t s);
 int launch_wgrad_unpack(const float* acc, float* dW, int C, int ntaps, long s_ci, long s_co, long s_t, cudaStream_t s);
 struct UnpackItem { const float* acc; float* dW; int ntaps; long s_ci, s_co, s_t; const float* dbacc; float* db; };
 struct UnpackList { int n; UnpackItem item[6]; };

@@ -19,6 +19,7 @@
 
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 namespace mdil {
 namespace wtc {
@@ -117,6 +118,11 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 struct Plan {
   int U, V, Ul, Vl, vblocks, nseg, L, units, halo;   // halo = 1 for 3 taps
 };
+struct Jobs {
+  WgradTcArgs a[3];
+  Plan pl[3];
+  int cta0[4];       // first CTA of every job; unused jobs are empty ranges at the end
+};
 
 // decode unit -> strip + segment
 struct Unit { int n, ru, rv, vb, ul0, Lu; };
@@ -135,8 +141,15 @@ __device__ __forceinline__ Unit decode_unit(int unit, const Plan& pl, int d) {
 
 template <int C>
 __global__ void __launch_bounds__(NWORK + 96, 1)
-wgrad_tc_kernel(const __grid_constant__ WgradTcArgs a, const Plan pl) {
+wgrad_tc_kernel(const __grid_constant__ Jobs jobs) {
   using K = Cfg<C>;
+  // up to three independent weight gradients (the three convolutions of a factorised pair) share one launch: CTAs
+  // [cta0[j], cta0[j+1]) work on job j.  Every CTA ends with ONE accumulator flush (red.global.add of [ntaps][C][C]),
+  // which at C = 128 costs as much as the main loop of a 148-CTA launch: three launches paid it three times.
+  const int job = (int)blockIdx.x >= jobs.cta0[2] ? 2 : ((int)blockIdx.x >= jobs.cta0[1] ? 1 : 0);
+  const WgradTcArgs& a = jobs.a[job];
+  const Plan& pl = jobs.pl[job];
+  const int bid = (int)blockIdx.x - jobs.cta0[job], nbid = jobs.cta0[job + 1] - jobs.cta0[job];
   constexpr int NST = K::NST;
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -183,7 +196,7 @@ wgrad_tc_kernel(const __grid_constant__ WgradTcArgs a, const Plan pl) {
       uint32_t q = 0;         // running stage-fill counter (identical on the producer side)
       uint32_t waited = 0;    // fills [0, waited) are known to have landed
       uint32_t started = 0;
-      for (int unit = blockIdx.x; unit < pl.units; unit += gridDim.x) {
+      for (int unit = bid; unit < pl.units; unit += nbid) {
         const Unit un = decode_unit(unit, pl, d);
         const uint32_t q0 = q;
         // chunk c (c = -halo .. Lu-1+halo) is fill q0 + c + halo.  Tap t of gradient chunk j reads the gradient of fill
@@ -243,7 +256,7 @@ wgrad_tc_kernel(const __grid_constant__ WgradTcArgs a, const Plan pl) {
     // before the first one is consumed (64 KB in flight per SM instead of 16 KB: the producers were latency-bound).
     constexpr int B = 1;
     struct FillDesc { size_t img; int u, rv, vb; uint32_t q; bool uok, interior, valid; };
-    int unit = blockIdx.x, f = 0, nfill = 0;
+    int unit = bid, f = 0, nfill = 0;
     uint32_t q = 0;
     Unit un;
     if (unit < pl.units) { un = decode_unit(unit, pl, d); nfill = un.Lu + 2 * pl.halo; }
@@ -251,7 +264,7 @@ wgrad_tc_kernel(const __grid_constant__ WgradTcArgs a, const Plan pl) {
       fd.valid = false;
       while (unit < pl.units) {
         if (f >= nfill) {
-          unit += gridDim.x;
+          unit += nbid;
           f = 0;
           if (unit < pl.units) { un = decode_unit(unit, pl, d); nfill = un.Lu + 2 * pl.halo; }
           continue;
@@ -368,7 +381,7 @@ wgrad_tc_kernel(const __grid_constant__ WgradTcArgs a, const Plan pl) {
     const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
     // Every CTA adds its partial [ntaps][C][C] into the same buffer: the walk over taps and 16-byte pieces is rotated by
     // the CTA index so that concurrent CTAs hit different addresses (same-address L2 atomics serialise).
-    const int rot = (int)blockIdx.x;
+    const int rot = bid;
     if (K::STACK) {
       // accumulator rows: [0,64) = A_hi channels, [64,128) = A_lo channels; columns [0,64) = G_hi, [64,128) = G_lo
       const int ci = (qd * 32 + lane) & 63;
@@ -471,11 +484,7 @@ __global__ void wgrad_unpack_p4_kernel(const UnpackP4List ul) {
   }
 }
 
-template <int C>
-int launch_c(const WgradTcArgs& a, cudaStream_t s) {
-  using K = Cfg<C>;
-  static_assert(K::SMEM <= 227 * 1024, "wgrad_tc shared memory budget");
-  static_assert(16 * K::NST + 32 <= 320, "wgrad_tc barrier header layout");
+static Plan make_plan(const WgradTcArgs& a, int nctas) {
   Plan pl;
   pl.U = a.vert ? a.H : a.W;
   pl.V = a.vert ? a.W : a.H;
@@ -484,8 +493,8 @@ int launch_c(const WgradTcArgs& a, cudaStream_t s) {
   pl.vblocks = cdiv(pl.Vl, TP);
   pl.halo = a.ntaps == 3 ? 1 : 0;
   const long strips = (long)a.N * a.dil * a.dil * pl.vblocks;
-  // split every strip into nseg segments of L chunks so that the persistent grid's busiest CTA has the least work:
-  // rounds = ceil(units / SMs), each unit costs L chunks plus the 2 * halo fills of its ends
+  // split every strip into nseg segments of L chunks so that the job's busiest CTA has the least work:
+  // rounds = ceil(units / CTAs), each unit costs L chunks plus the 2 * halo fills of its ends
   int best_nseg = 1;
   double best_cost = 1e30;
   for (int nseg = 1; nseg <= pl.Ul; ++nseg) {
@@ -493,35 +502,66 @@ int launch_c(const WgradTcArgs& a, cudaStream_t s) {
     if (L < 4 && nseg > 1) break;
     const int ns = cdiv(pl.Ul, L);
     const long units = strips * ns;
-    const double cost = (double)cdiv((int)units, kNumSMs) * (L + 2 * pl.halo + 1);
+    const double cost = (double)cdiv((int)units, nctas) * (L + 2 * pl.halo + 1);
     if (cost < best_cost - 1e-9) { best_cost = cost; best_nseg = ns; }
   }
   pl.L = cdiv(pl.Ul, best_nseg);
   pl.nseg = cdiv(pl.Ul, pl.L);
-  const long units = strips * pl.nseg;
-  MDIL_REQUIRE(units > 0 && units < (1L << 30), "wgrad_tc: unit count");
-  pl.units = (int)units;
-  const int grid = (int)(units < kNumSMs ? units : kNumSMs);
+  pl.units = (int)(strips * pl.nseg);
+  return pl;
+}
+
+template <int C>
+int launch_c(const WgradTcArgs* a, int n, cudaStream_t s) {
+  using K = Cfg<C>;
+  static_assert(K::SMEM <= 227 * 1024, "wgrad_tc shared memory budget");
+  static_assert(16 * K::NST + 32 <= 320, "wgrad_tc barrier header layout");
+  // CTA shares: the main loop costs the same for every job (same pixels: the producers bound it), the accumulator flush
+  // scales with the tap count (measured at C = 128: flush of three taps ~ one main loop)
+  double cost[3] = {0, 0, 0}, tot = 0;
+  for (int j = 0; j < n; ++j) { cost[j] = 1.0 + (C == 128 ? 0.85 : 0.3) * a[j].ntaps / 3.0; tot += cost[j]; }
+  Jobs jobs;
+  memset(&jobs, 0, sizeof(jobs));
+  int used = 0;
+  for (int j = 0; j < n; ++j) {
+    int share = j == n - 1 ? kNumSMs - used : (int)(kNumSMs * cost[j] / tot + 0.5);
+    if (share < 1) share = 1;
+    jobs.a[j] = a[j];
+    jobs.pl[j] = make_plan(a[j], share);
+    MDIL_REQUIRE(jobs.pl[j].units > 0, "wgrad_tc: unit count");
+    if (jobs.pl[j].units < share) share = jobs.pl[j].units;
+    jobs.cta0[j] = used;
+    used += share;
+  }
+  for (int j = n; j <= 3; ++j) jobs.cta0[j] = used;
   MDIL_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM));
-  wgrad_tc_kernel<C><<<grid, NWORK + 96, K::SMEM, s>>>(a, pl);
+  wgrad_tc_kernel<C><<<used, NWORK + 96, K::SMEM, s>>>(jobs);
   MDIL_LAUNCH_CHECK();
   return 0;
 }
 
 }  // namespace wtc
 
-int launch_wgrad_tc(const WgradTcArgs& a_in, cudaStream_t s) {
+int launch_wgrad_tc_multi(const WgradTcArgs* a_in, int n, cudaStream_t s) {
   static const int trace = getenv("MDIL_TC_TRACE") != nullptr ? 1 : 0;
-  WgradTcArgs a = a_in;
-  a.trace = trace;
-  MDIL_REQUIRE(a.ntaps == 1 || a.ntaps == 3, "wgrad_tc: 1 or 3 taps");
-  MDIL_REQUIRE(a.dWacc != nullptr && ((uintptr_t)a.dWacc & 15) == 0, "wgrad_tc: accumulator buffer");
-  switch (a.C) {
-    case 128: return wtc::launch_c<128>(a, s);
-    case 64: return wtc::launch_c<64>(a, s);
+  if (n == 0) return 0;
+  MDIL_REQUIRE(n >= 1 && n <= 3, "wgrad_tc: 1 to 3 jobs per launch");
+  WgradTcArgs a[3];
+  for (int j = 0; j < n; ++j) {
+    a[j] = a_in[j];
+    a[j].trace = trace;
+    MDIL_REQUIRE(a[j].ntaps == 1 || a[j].ntaps == 3, "wgrad_tc: 1 or 3 taps");
+    MDIL_REQUIRE(a[j].dWacc != nullptr && ((uintptr_t)a[j].dWacc & 15) == 0, "wgrad_tc: accumulator buffer");
+    MDIL_REQUIRE(a[j].C == a[0].C, "wgrad_tc: the jobs of one launch share C");
+  }
+  switch (a[0].C) {
+    case 128: return wtc::launch_c<128>(a, n, s);
+    case 64: return wtc::launch_c<64>(a, n, s);
     default: return set_error(-2, "wgrad_tc: C must be 64 or 128", __FILE__, __LINE__);
   }
 }
+
+int launch_wgrad_tc(const WgradTcArgs& a, cudaStream_t s) { return launch_wgrad_tc_multi(&a, 1, s); }
 
 int launch_wgrad_unpack_multi(const UnpackList& ul, int C, cudaStream_t s) {
   if (ul.n == 0) return 0;

@@ -11,6 +11,22 @@ cols = [("gpu__time_duration.sum", "time"), ("dram__bytes_read.sum", "dram_rd"),
         ("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "fma_pipe%"),
         ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor_pipe%"),
         ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps_active%"),
+        ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_active%"),
+        ("smsp__warps_eligible.avg.per_cycle_active", "eligible_warps"),
+        ("smsp__inst_executed.sum", "warp_insts"),
+        ("l1tex__data_bank_reads.avg.pct_of_peak_sustained_elapsed", "smem_bank_rd%"),
+        ("l1tex__data_bank_writes.avg.pct_of_peak_sustained_elapsed", "smem_bank_wr%"),
+        ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smem_lsu_wavefronts"),
+        ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem_bank_conflicts"),
+        ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "stall_long_sb"),
+        ("smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "stall_short_sb"),
+        ("smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "stall_wait"),
+        ("smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "stall_barrier"),
+        ("smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio", "stall_mio"),
+        ("smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio", "stall_lg"),
+        ("smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "stall_math"),
+        ("smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio", "stall_no_inst"),
+        ("smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio", "stall_not_selected"),
         ("launch__registers_per_thread", "regs"), ("launch__shared_mem_per_block_dynamic", "dyn_smem"),
         ("launch__grid_size", "grid")]
 agg = collections.OrderedDict()

@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="crops per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the PyTorch-eager (cuDNN) baseline leg")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying the captured step")
     ap.add_argument("--ncu-step", action="store_true",
                     help="profiling aid: after warm-up run ONE step between cudaProfilerStart/Stop and exit "
                          "(use with ncu --profile-from-start off); prints no bench line")
@@ -320,15 +321,6 @@ def run_ours(args):
     prefetch = DevicePrefetcher(dev)
     prefetch.put(images_h, labels_h)
 
-    def step_e2e():
-        # every step consumes a batch copied from pinned host memory; the copy of the NEXT batch is issued on the
-        # prefetcher's side stream before this step's kernels, as a DataLoader-fed training loop would
-        x, y = prefetch.get()
-        prefetch.put(images_h, labels_h)
-        out = trainer.step(x, y)
-        loss = out[0] if isinstance(out, tuple) else out
-        return float(loss)  # device -> host read of the step's result
-
     def barrier():
         if world > 1:
             dist.barrier()
@@ -356,20 +348,67 @@ def run_ours(args):
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
         return
-    # ---- timed region (device-resident inputs), clocks sampled during it, pair-kernel launches bracketed by events
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    # ---- kernel launches of one step, and the per-kind CUDA-event timing of the fused pair kernels (roofline leg):
+    # a few eager steps with the library's launch profiling on
     launches0 = _lib.launches()
     lib.mdil_profile_begin()
-    ms_total = timed(step_resident, args.steps)
+    prof_steps = 5
+    barrier()
+    for _ in range(prof_steps):
+        step_resident()
+    barrier()
     nk = 12
     tot = (ctypes.c_float * nk)()
     cnt = (ctypes.c_int * nk)()
     lib.mdil_profile_end(tot, cnt, nk)
-    launches = _lib.launches() - launches0
+    launches_per_step = (_lib.launches() - launches0) // prof_steps
+
+    # ---- the step as the product runs it: captured once in a CUDA graph and replayed (one host call per step); falls
+    # back to host-side launches where the trainer cannot be captured (step 3: per-parameter optimiser step counts)
+    graphed = None
+    if not args.no_graph and args.workload in ("step1", "step2"):
+        try:
+            from mdil_ss_b200.train_step import GraphedStep
+            graphed = GraphedStep(trainer, images, labels)
+        except Exception as exc:   # noqa: BLE001
+            if rank == 0:
+                print(f"bench.py: CUDA-graph capture unavailable ({exc!r}); launching from the host", file=sys.stderr)
+            graphed = None
+    graph_flags = torch.tensor([1.0 if graphed is not None else 0.0], device=dev)
+    if world > 1:
+        dist.all_reduce(graph_flags, op=dist.ReduceOp.MIN)     # every rank or none (the collectives must line up)
+    if float(graph_flags) < 1.0:
+        graphed = None
+
+    def run_step(x, y):
+        return graphed.step(x, y) if graphed is not None else trainer.step(x, y)
+
+    def step_value():
+        return run_step(images, labels)
+
+    def step_e2e():
+        # every step consumes a batch copied from pinned host memory; the copy of the NEXT batch is issued on the
+        # prefetcher's side stream before this step's kernels, as a DataLoader-fed training loop would
+        x, y = prefetch.get()
+        prefetch.put(images_h, labels_h)
+        out = run_step(x, y)
+        loss = out[0] if isinstance(out, tuple) else out
+        return float(loss)  # device -> host read of the step's result
+
+    for _ in range(2):
+        step_value()
+    # ---- timed region (device-resident inputs), clocks sampled during it
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_total = timed(step_value, args.steps)
+    launches = launches_per_step * args.steps
     clocks = sampler.stop() if rank == 0 else None
     value = world * crops_per_step * args.steps / (ms_total / 1e3)
+    # tot[] / cnt[] cover prof_steps eager steps
+    for i in range(nk):
+        tot[i] = tot[i] * args.steps / prof_steps
+        cnt[i] = cnt[i] * args.steps // prof_steps
 
     # ---- end-to-end: host buffers, H2D of the inputs and D2H of the loss inside the timed region
     for _ in range(2):
@@ -419,7 +458,9 @@ def run_ours(args):
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                         "h2d_bytes_per_step": images_h.numel() * 4 + labels_h.numel() * 8, "d2h_bytes_per_step": 4},
-                "gpu_launches": int(launches), "roofline": roofline}
+                "gpu_launches": int(launches), "cuda_graph": graphed is not None,
+                "gpu_launches_note": "kernels of this library inside the timed region = launches of one step (counted on an eager step) x steps; with cuda_graph the step is replayed from one captured graph",
+                "roofline": roofline}
         if not args.no_cpu_baseline and world == 1:   # CPU baseline: rank 0 at N=1 only
             cpu_steps = 2 if args.workload == "step1" else 1
             v, ms, cores = time_cpu(args.workload, 1, cpu_steps, 1)

@@ -198,6 +198,11 @@ int mdil_cotransform(const unsigned char* img, const unsigned char* lab, int N, 
 int mdil_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
                    float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
 
+/* The same update with the step counter and the learning rate in DEVICE memory (state: float[4] = steps taken so far, lr,
+ * two scratch words), so that an optimiser step captured in a CUDA graph advances its own bias corrections on replay. */
+int mdil_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float* state, float beta1,
+                       float beta2, float eps, float weight_decay, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,7 +23,7 @@ EXPORTS = [
     "mdil_outconv_fwd", "mdil_outconv_bwd",
     "mdil_ce2d_fwd_bwd", "mdil_ce2d_scale", "mdil_kd_fwd_bwd", "mdil_scale_by_device_scalar",
     "mdil_argmax_confusion", "mdil_adam_step", "mdil_launch_count", "mdil_profile_begin", "mdil_profile_end",
-    "mdil_cotransform",
+    "mdil_cotransform", "mdil_adam_step_dev",
 ]
 
 
@@ -103,6 +103,7 @@ def _declare(lib) -> None:
     lib.mdil_argmax_confusion.argtypes = [vp, vp, i, i, i, i, vp, vp, vp]
     lib.mdil_profile_end.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_int), i]
     lib.mdil_adam_step.argtypes = [vp, vp, vp, vp, sz, f, f, f, f, f, i, f, vp]
+    lib.mdil_adam_step_dev.argtypes = [vp, vp, vp, vp, sz, vp, f, f, f, f, f, vp]
     lib.mdil_cotransform.argtypes = [vp, vp, i, i, i, i, i, vp, i, vp, i, vp, vp, vp, i, vp, vp, vp]
     non_int = {"mdil_version", "mdil_last_error_string", "mdil_launch_count", "mdil_nb1d_packed_floats",
                "mdil_nb1d_fwd_workspace_bytes", "mdil_nb1d_bwd_workspace_bytes", "mdil_down_packed_floats",

@@ -738,4 +738,9 @@ int mdil_adam_step(float* param, const float* grad, float* exp_avg, float* exp_a
   return launch_adam(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, S(stream));
 }
 
+int mdil_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float* state, float beta1,
+                       float beta2, float eps, float weight_decay, float grad_scale, void* stream) {
+  return launch_adam_dev(param, grad, exp_avg, exp_avg_sq, n, state, beta1, beta2, eps, weight_decay, grad_scale, S(stream));
+}
+
 }  // extern "C"

@@ -377,6 +377,39 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
   }
 }
 
+// CUDA-graph-safe variant: the step counter and the learning rate live in device memory (state[0] = steps taken so far,
+// state[1] = lr; state[2], state[3] receive step_size and sqrt(bias_correction2)), so a captured optimiser step advances
+// its own bias corrections on every replay.  Corrections in double, as torch.optim.Adam computes them.
+__global__ void adam_prepare_kernel(float* __restrict__ state, float b1, float b2) {
+  const double step = (double)state[0] + 1.0;
+  state[0] = (float)step;
+  state[2] = (float)((double)state[1] / (1.0 - pow((double)b1, step)));
+  state[3] = (float)sqrt(1.0 - pow((double)b2, step));
+}
+__global__ void __launch_bounds__(256)
+adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, size_t n,
+                const float* __restrict__ state, float b1, float b2, float eps, float wd, float grad_scale) {
+  const float step_size = state[2], bc2_sqrt = state[3];
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float pi = p[i];
+    float gi = g[i] * grad_scale + wd * pi;
+    float mi = b1 * m[i] + (1.f - b1) * gi;
+    float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - step_size * (mi / denom);
+  }
+}
+int launch_adam_dev(float* param, const float* grad, float* m, float* v, size_t n, float* state, float b1, float b2, float eps,
+                    float wd, float grad_scale, cudaStream_t s) {
+  adam_prepare_kernel<<<1, 1, 0, s>>>(state, b1, b2);
+  MDIL_LAUNCH_CHECK();
+  adam_dev_kernel<<<ew_grid(n, 256), 256, 0, s>>>(param, grad, m, v, n, state, b1, b2, eps, wd, grad_scale);
+  MDIL_LAUNCH_CHECK();
+  return 0;
+}
+
 int launch_adam(float* param, const float* grad, float* m, float* v, size_t n, float lr, float b1, float b2, float eps,
                 float wd, int step, float grad_scale, cudaStream_t s) {
   // bias corrections in double on the host, as torch.optim.Adam computes them in Python floats (1 - 0.999f carries a

@@ -47,6 +47,9 @@ int launch_scale(float* x, size_t n, const double* inv_den /*nullable: multiply 
                  cudaStream_t s);
 int launch_adam(float* param, const float* grad, float* m, float* v, size_t n, float lr, float b1, float b2, float eps,
                 float wd, int step, float grad_scale, cudaStream_t s);
+// state: device float[4] = {steps taken, lr, scratch, scratch}: graph-capturable (see elementwise.cu)
+int launch_adam_dev(float* param, const float* grad, float* m, float* v, size_t n, float* state, float b1, float b2, float eps,
+                    float wd, float grad_scale, cudaStream_t s);
 
 // ---------------------------------------------------------------- conv_taps.cu
 constexpr int kMaxTaps = 9;

@@ -99,6 +99,7 @@ class FlatAdam:
 
     def __init__(self, groups: Sequence[dict], lr: float = 5e-4, betas=(0.9, 0.999), eps: float = 1e-8,
                  weight_decay: float = 1e-4):
+        self.graph_safe = False      # see enable_graph_safe()
         self.groups = []
         for g in groups:
             params = [p for p in g["params"] if p.requires_grad]
@@ -114,10 +115,36 @@ class FlatAdam:
     def zero_grad(self) -> None:
         self.reducer.zero_grad()
 
+    def enable_graph_safe(self) -> None:
+        """Keep the step counter and the learning rate of every group in device memory (mdil_adam_step_dev) so that
+        ``step()`` can be captured in a CUDA graph and replayed (train_step.GraphedStep).  Requires that every parameter
+        of a group receives a gradient in every step (true for steps 1 and 2, not for step 3's KD step)."""
+        if self.graph_safe:
+            return
+        for g in self.groups:
+            buf = g["buf"]
+            if not buf.data.is_cuda:
+                raise RuntimeError("FlatAdam.enable_graph_safe: CUDA parameters only")
+            steps = g.get("steps", [0] * len(buf.params))
+            if len(set(steps)) > 1:
+                raise RuntimeError("FlatAdam.enable_graph_safe: the parameters of a group have different step counts")
+            g["dev_state"] = torch.tensor([float(steps[0]), float(g["lr"]), 0.0, 0.0], device=buf.data.device,
+                                          dtype=torch.float32)
+        self.graph_safe = True
+
+    def _sync_steps_from_device(self) -> None:
+        if self.graph_safe:
+            for g in self.groups:
+                n = int(round(float(g["dev_state"][0])))
+                g["steps"] = [n] * len(g["buf"].params)
+            self.step_count = max([g["steps"][0] for g in self.groups] or [0])
+
     def set_lr_factor(self, factor: float) -> None:
         """LambdaLR semantics (train_new_task_step2.py:244-245): lr = initial_lr * factor."""
         for g in self.groups:
             g["lr"] = g["initial_lr"] * factor
+            if self.graph_safe:
+                g["dev_state"][1] = g["lr"]        # read by the captured step on its next replay
 
     def step(self, allreduce: bool = True) -> None:
         scale = self.reducer.allreduce() if allreduce else 1.0
@@ -126,6 +153,15 @@ class FlatAdam:
         for g in self.groups:
             buf = g["buf"]
             steps = g.setdefault("steps", [0] * len(buf.params))
+            if self.graph_safe:
+                if any(getattr(p, "_mdil_grad_fresh", False) for p in buf.params):
+                    raise RuntimeError("FlatAdam (graph-safe mode): a parameter received no gradient in this step")
+                with torch.cuda.device_of(buf.data):
+                    L.check(L.lib().mdil_adam_step_dev(buf.data.data_ptr(), buf.grad.data_ptr(), g["exp_avg"].data_ptr(),
+                                                       g["exp_avg_sq"].data_ptr(), buf.numel(), g["dev_state"].data_ptr(),
+                                                       b1, b2, self.eps, self.weight_decay, scale,
+                                                       torch.cuda.current_stream().cuda_stream), "mdil_adam_step_dev")
+                continue
             if buf.data.is_cuda:
                 # torch.optim.Adam skips parameters whose .grad is None, which is what the drivers' zero_grad() leaves
                 # behind for tensors no loss reached (step 3's KD step never touches the new domain's tensors,
@@ -166,6 +202,7 @@ class FlatAdam:
 
     # ---- torch.optim.Adam's checkpoint format (the drivers save optimizer.state_dict(), train_new_task_step2.py:380)
     def state_dict(self) -> dict:
+        self._sync_steps_from_device()
         state, groups, idx = {}, [], 0
         for g in self.groups:
             buf = g["buf"]
@@ -204,6 +241,13 @@ class FlatAdam:
                         g["exp_avg"][o:o + n].copy_(st["exp_avg"].reshape(-1))
                         g["exp_avg_sq"][o:o + n].copy_(st["exp_avg_sq"].reshape(-1))
         self.step_count = max([max(g.get("steps", [0]) or [0]) for g in self.groups] or [0])
+        if self.graph_safe:
+            for g in self.groups:
+                steps = g["steps"]
+                if len(set(steps)) > 1:
+                    raise RuntimeError("FlatAdam (graph-safe mode): loaded state has per-parameter step counts")
+                g["dev_state"][0] = float(steps[0])
+                g["dev_state"][1] = float(g["lr"])
 
     def _bump_versions(self) -> None:
         # the parameters changed in place through the flat buffer: bump the version counters that the

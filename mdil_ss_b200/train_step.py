@@ -179,3 +179,40 @@ class MultiTaskTrainer:
     def step(self, batches):
         """``batches[i] = (images_i, labels_i)`` for dataset i; returns the list of CE losses."""
         return [self.visit(ind, images, labels) for ind, (images, labels) in enumerate(batches)]
+
+
+class GraphedStep:
+    """One training iteration captured in a CUDA graph and replayed: ~410 kernel launches, the weight
+    re-packing, the gradient all-reduce and the fused Adam become ONE host call, which takes the Python / launch overhead
+    (~10 ms per step from idle) off the critical path -- what limits end-to-end scaling when 8 ranks share one host.
+
+    ``GraphedStep(trainer, images, labels)`` warms the trainer up on the given (static-shape) batch, switches its FlatAdam
+    to device-side step counters and captures ``trainer.step``; ``step(images, labels)`` copies the new batch into the
+    captured input buffers (device-to-device) and replays.  The returned loss tensors are the captured ones (read them
+    after the replay, e.g. every k steps).  Usable where every trainable parameter receives a gradient in every step
+    (Step1Trainer, Step2Trainer); Step3Trainer's KD step is not (FlatAdam raises).  NCCL collectives inside the step are
+    captured with it."""
+
+    def __init__(self, trainer, images: torch.Tensor, labels: torch.Tensor, warmup: int = 3):
+        self.trainer = trainer
+        self.static_images = images.clone()
+        self.static_labels = labels.clone()
+        trainer.optimizer.enable_graph_safe()
+        side = torch.cuda.Stream(images.device)
+        side.wait_stream(torch.cuda.current_stream(images.device))
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):        # also finishes every lazy initialisation (function attributes, caches)
+                trainer.step(self.static_images, self.static_labels)
+        torch.cuda.current_stream(images.device).wait_stream(side)
+        torch.cuda.synchronize(images.device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.outputs = trainer.step(self.static_images, self.static_labels)
+
+    def step(self, images: torch.Tensor, labels: torch.Tensor):
+        if images.data_ptr() != self.static_images.data_ptr():
+            self.static_images.copy_(images, non_blocking=True)
+        if labels.data_ptr() != self.static_labels.data_ptr():
+            self.static_labels.copy_(labels, non_blocking=True)
+        self.graph.replay()
+        return self.outputs

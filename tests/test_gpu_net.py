@@ -474,3 +474,49 @@ def test_device_prefetcher_round_trip():
         assert torch.equal(xd.cpu(), x) and torch.equal(yd.cpu(), y)
     with pytest.raises(RuntimeError):
         pf.get()
+
+
+def test_graphed_step_equals_eager_steps():
+    """train_step.GraphedStep: K replays of the captured iteration (device-side Adam step counter, re-packed weights,
+    BatchNorm buffers) move the network like K eager iterations on the same batch -- up to the summation order of the
+    floating-point atomics -- and the optimiser's checkpoint reports the replayed step count."""
+    import copy
+    from mdil_ss_b200.erfnet_RA_parallel import Net
+    from mdil_ss_b200.train_step import GraphedStep, Step1Trainer, class_weights
+    sd = pretrained_sd(golden("pretrained_eval.npz"))
+    gen = torch.Generator().manual_seed(77)
+    x = torch.rand(2, 3, 64, 128, generator=gen).to(DEV)
+    y = torch.randint(0, 20, (2, 1, 8, 16), generator=gen).repeat_interleave(8, 2).repeat_interleave(8, 3).to(DEV)
+    nets = []
+    for _ in range(2):
+        net = Net([20], 1, 0)
+        net.load_state_dict(sd)
+        for m in net.modules():                      # identical dropout streams are not reproducible across the two runs
+            if isinstance(m, torch.nn.Dropout2d):
+                m.p = 0.0
+        nets.append(net.to(DEV))
+    eager = Step1Trainer(nets[0], class_weights("cityscapes", DEV))
+    graph = Step1Trainer(nets[1], class_weights("cityscapes", DEV))
+    K, warm = 4, 2
+    losses_e = [float(eager.step(x, y)) for _ in range(warm + K)]
+    g = GraphedStep(graph, x, y, warmup=warm)        # warm eager steps, then capture (capture itself does not execute)
+    losses_g = []
+    for _ in range(K):
+        out = g.step(x, y)
+        losses_g.append(float(out))
+    assert all(np.isfinite(losses_g))
+    np.testing.assert_allclose(losses_g, losses_e[warm:], rtol=2e-3)
+    pe, pg = dict(nets[0].named_parameters()), dict(nets[1].named_parameters())
+    num = den = 0.0
+    for n in pe:
+        if n.endswith(".bias") and "bn" not in n:
+            continue     # conv biases in front of a train-mode BatchNorm: zero gradient, Adam moves them by rounding noise
+        d0 = sd[n].to(DEV).double()
+        num += float(((pg[n].double() - d0) - (pe[n].double() - d0)).pow(2).sum())
+        den += float((pe[n].double() - d0).pow(2).sum())
+    assert (num / den) ** 0.5 <= 1e-1, f"parameter movement after {warm + K} steps: graph vs eager rel L2 {(num / den) ** 0.5:.2e}"
+    st = graph.optimizer.state_dict()["state"]
+    assert int(float(st[0]["step"])) == warm + K
+    be, bg = dict(nets[0].named_buffers()), dict(nets[1].named_buffers())
+    k = "encoder.layers.0.bn_ini.0.num_batches_tracked"
+    assert int(be[k]) == int(bg[k]) == warm + K

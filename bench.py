@@ -484,8 +484,17 @@ def run_ours(args):
             line["gpu_baseline"] = gb
         print(json.dumps(line), flush=True)
     if world > 1:
+        # Teardown: the captured graph holds NCCL kernels; destroying the process group under it was seen to hang
+        # (2-GPU run, after the bench line had been printed).  Drop the graph, drain the device, and leave without the
+        # collective teardown: every rank has passed the barrier, nothing is in flight.
         dist.barrier()
-        dist.destroy_process_group()
+        graphed = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

@@ -72,13 +72,13 @@ template <int C> struct Cfg {
 // header offsets (bytes from the 1024-aligned header base)
 constexpr uint32_t OFF_WFULL = 0;        // [<= 14]
 constexpr uint32_t OFF_WEMPTY = 128;     // [<= 4]
-constexpr uint32_t OFF_INFULL = 160;     // [NBUF][SLABS]: <= 4
-constexpr uint32_t OFF_MIDFULL = 192;    // [NBUF][NKC]: <= 8
-constexpr uint32_t OFF_BUFFREE = 256;    // [NBUF]: <= 3
-constexpr uint32_t OFF_ACC1FULL = 288;   // [2]
-constexpr uint32_t OFF_ACC2FULL = 304;   // [2]
-constexpr uint32_t OFF_ACC2FREE = 320;   // [2]
-constexpr uint32_t OFF_TMEMSLOT = 336;
+constexpr uint32_t OFF_INFULL = 160;     // [NBUF][NKC]: <= 8 (one per 32-channel chunk of the input tile)
+constexpr uint32_t OFF_MIDFULL = 224;    // [NBUF][NKC]: <= 8
+constexpr uint32_t OFF_BUFFREE = 288;    // [NBUF]: <= 3
+constexpr uint32_t OFF_ACC1FULL = 320;   // [2]
+constexpr uint32_t OFF_ACC2FULL = 336;   // [2]
+constexpr uint32_t OFF_ACC2FREE = 352;   // [2]
+constexpr uint32_t OFF_TMEMSLOT = 368;
 constexpr uint32_t OFF_B1 = 512;         // float [C]
 constexpr uint32_t OFF_B2 = 1024;        // float [C]: b2 + adapter bias
 constexpr uint32_t OFF_TRACE = 2816;     // long long [30] (TRACE instantiations only)
@@ -280,7 +280,7 @@ pair_h3_kernel(const __grid_constant__ PairArgs a, const __grid_constant__ Geo g
   if (tid == 0) {
     for (int i = 0; i < NSTAGE; ++i) mbar_init(hdr + OFF_WFULL + 8 * i, 1);
     if (!K::RESIDENT) for (int i = 0; i < NSTAGE; ++i) mbar_init(hdr + OFF_WEMPTY + 8 * i, (uint32_t)CL);
-    for (int i = 0; i < NBUF * SLABS; ++i) mbar_init(hdr + OFF_INFULL + 8 * i, N_LOAD);
+    for (int i = 0; i < NBUF * NKC; ++i) mbar_init(hdr + OFF_INFULL + 8 * i, N_LOAD);
     for (int i = 0; i < NBUF * NKC; ++i) mbar_init(hdr + OFF_MIDFULL + 8 * i, 128);   // the 4 warps that own the chunk
     for (int i = 0; i < NBUF; ++i) mbar_init(hdr + OFF_BUFFREE + 8 * i, 1);
     for (int i = 0; i < 2; ++i) {
@@ -397,9 +397,9 @@ pair_h3_kernel(const __grid_constant__ PairArgs a, const __grid_constant__ Geo g
       int g = 0;
 #pragma unroll
       for (int j = 0; j < NKC; ++j) {
-        if ((j & 1) == 0) {
+        {   // the loader fills the tile one 32-channel chunk at a time: the conv starts on the first chunk
           H3_T0();
-          mbar_wait(hdr + OFF_INFULL + 8 * (b * SLABS + (j >> 1)), (uint32_t)(use & 1));
+          mbar_wait(hdr + OFF_INFULL + 8 * (b * NKC + j), (uint32_t)(use & 1));
           H3_T1(0);
           tc_fence_after();
         }
@@ -457,23 +457,20 @@ pair_h3_kernel(const __grid_constant__ PairArgs a, const __grid_constant__ Geo g
   } else if (warp >= W_LOAD0) {
     // ============================================================ loader warps (8..13)
     // Per tile: (1) thread lt < INROWS computes the pixel index of input row lt once (-1: outside the image = zero
-    // padding) into a double-buffered shared table; (2) item = (row, 4 channels): a pass covers 192 items = RPP rows, a
-    // batch = PB passes; the batches of all tiles form one stream in which the loads of batch g+1 are issued before batch g
-    // is converted (register double buffer), across tile boundaries too; (3) fp32 -> BN+ReLU prologue -> 16-bit hi/lo
-    // halves -> swizzled K-major operand rows.
+    // padding) into a double-buffered shared table; (2) item = (row, 4 channels of one 32-channel chunk); a batch = one
+    // chunk of the whole tile; the batches of all tiles form one stream in which the loads of batch g+1 are issued before
+    // batch g is converted (register double buffer), across tile boundaries too; (3) fp32 -> BN+ReLU prologue -> 16-bit
+    // hi/lo halves -> swizzled K-major operand rows; every chunk has its own "input full" barrier.
     constexpr int IN_MAX = K::IN_MAX;
     const int lt = tid - W_LOAD0 * 32;
-    constexpr int C4 = C / 4;                 // items per row
-    constexpr int RPP = N_LOAD / C4;          // rows per pass: 12 (C = 64), 6 (C = 128)
-    constexpr int PASSES = (IN_MAX + RPP - 1) / RPP;
-    constexpr int PB = 7;                     // passes per batch
-    constexpr int NB = (PASSES + PB - 1) / PB;
-    const int c4 = lt % C4, rsub = lt / C4;
-    const int slab = c4 >> 4;                                  // 64-channel operand row
-    const uint32_t chunk16 = (uint32_t)(c4 & 15) >> 1, half8 = (uint32_t)(c4 & 1) * 8u;
+    // CHUNK-MAJOR order: a batch = one 32-channel chunk of the whole tile (8 threads x 128-bit per row, 24 rows per pass,
+    // 7 passes), so that the first conv can start on chunk 0 while the later chunks are still being loaded
+    constexpr int RPP = N_LOAD / 8;           // rows per pass: 24
+    constexpr int PB = (IN_MAX + RPP - 1) / RPP;   // passes per batch = per chunk: 7
+    constexpr int NB = NKC;                   // batches per tile
+    const int c4 = lt & 7, rsub = lt >> 3;    // 4-channel group inside the chunk, row inside the pass
+    const uint32_t half8 = (uint32_t)(c4 & 1) * 8u;
     const bool pro = a.in_scale != nullptr;
-    float4 sc = make4(1.f), sh = make4(0.f);
-    if (pro) { sc = ldg4(a.in_scale + c4 * 4); sh = ldg4(a.in_shift + c4 * 4); }
     int my_iu = 0, my_r = 0, my_iv = 0;          // tile-independent decomposition of input row lt: [iu][class][iv]
     const bool my_row = lt < geo.INROWS;
     if (my_row) { my_iu = lt / RT; const int rem = lt % RT; my_r = rem / TVH; my_iv = rem % TVH; }
@@ -497,7 +494,7 @@ pair_h3_kernel(const __grid_constant__ PairArgs a, const __grid_constant__ Geo g
         pixtab[(t & 1) * IN_MAX_ALL + lt] = pix;
       }
       { H3_T0(); named_bar_sync(2, N_LOAD); H3_T1(3); }
-      src = a.in + (size_t)ti.n * a.H * a.W * C + c4 * 4;
+      src = a.in + (size_t)ti.n * a.H * a.W * C + c4 * 4;      // + 32 * chunk at issue time
     };
     auto issue = [&](float4 (&x)[PB], uint32_t& valid, int g) {
       const int t = g / NB, bt = g - t * NB;
@@ -506,12 +503,12 @@ pair_h3_kernel(const __grid_constant__ PairArgs a, const __grid_constant__ Geo g
       valid = 0;
 #pragma unroll
       for (int p = 0; p < PB; ++p) {
-        const int row = (bt * PB + p) * RPP + rsub;
+        const int row = p * RPP + rsub;            // every batch walks all rows of the tile
         x[p] = make4(0.f);
         if (row < IN_MAX) {
           const int pix = ptab[row];
           if (pix >= 0) {
-            x[p] = ldg4(src + (size_t)pix * C);
+            x[p] = ldg4(src + (size_t)pix * C + bt * KCH);
             valid |= 1u << p;
           }
         }
@@ -521,30 +518,32 @@ pair_h3_kernel(const __grid_constant__ PairArgs a, const __grid_constant__ Geo g
       const int t = g / NB, bt = g - t * NB;
       const int b = t % NBUF, use = t / NBUF;
       if (bt == 0 && t >= NBUF) { H3_T0(); mbar_wait(hdr + OFF_BUFFREE + 8 * b, (uint32_t)((use - 1) & 1)); H3_T1(0); }
-      unsigned char* buf = gen + K::HDR_BYTES + (size_t)b * K::BUF_BYTES + (size_t)slab * K::SLAB_BYTES;
+      unsigned char* buf = gen + K::HDR_BYTES + (size_t)b * K::BUF_BYTES + (size_t)(bt >> 1) * K::SLAB_BYTES;
+      const uint32_t chunk16 = (uint32_t)((bt & 1) * 4 + (c4 >> 1));     // 16-byte chunk of the 128-byte operand row
+      float4 sc = make4(1.f), sh = make4(0.f);
+      if (pro) { sc = ldg4(a.in_scale + bt * KCH + c4 * 4); sh = ldg4(a.in_shift + bt * KCH + c4 * 4); }
 #pragma unroll
-      for (int p = 0; p < PB; ++p) {
-        const int row = (bt * PB + p) * RPP + rsub;
-        if (row >= geo.INROWS) continue;
+      for (int p = 0; p < PB; ++p) {       // branch-free: the seven items interleave in the instruction stream
+        const int row = p * RPP + rsub;            // every batch walks all rows of the tile
         float4 v4 = x[p];
-        if (pro && ((valid >> p) & 1u)) {
-          v4.x = fmaxf(fmaf(v4.x, sc.x, sh.x), 0.f);
-          v4.y = fmaxf(fmaf(v4.y, sc.y, sh.y), 0.f);
-          v4.z = fmaxf(fmaf(v4.z, sc.z, sh.z), 0.f);
-          v4.w = fmaxf(fmaf(v4.w, sc.w, sh.w), 0.f);
+        if (pro) {
+          const bool ok = (valid >> p) & 1u;       // padding rows stay zero
+          v4.x = ok ? fmaxf(fmaf(v4.x, sc.x, sh.x), 0.f) : 0.f;
+          v4.y = ok ? fmaxf(fmaf(v4.y, sc.y, sh.y), 0.f) : 0.f;
+          v4.z = ok ? fmaxf(fmaf(v4.z, sc.z, sh.z), 0.f) : 0.f;
+          v4.w = ok ? fmaxf(fmaf(v4.w, sc.w, sh.w), 0.f) : 0.f;
         }
         uint2 hi, lo;
         split2<FMT>(v4.x, v4.y, hi.x, lo.x);
         split2<FMT>(v4.z, v4.w, hi.y, lo.y);
         const uint32_t off = (uint32_t)row * 128u + (((chunk16 ^ ((uint32_t)row & 7u)) << 4) | half8);
-        *reinterpret_cast<uint2*>(buf + off) = hi;
-        *reinterpret_cast<uint2*>(buf + off + K::IMG_BYTES) = lo;
+        if (row < geo.INROWS) {
+          *reinterpret_cast<uint2*>(buf + off) = hi;
+          *reinterpret_cast<uint2*>(buf + off + K::IMG_BYTES) = lo;
+        }
       }
-      if (bt == NB - 1) {
-        fence_proxy_async();
-#pragma unroll
-        for (int sl = 0; sl < SLABS; ++sl) mbar_arrive(hdr + OFF_INFULL + 8 * (b * SLABS + sl));
-      }
+      fence_proxy_async();
+      mbar_arrive(hdr + OFF_INFULL + 8 * (b * NKC + bt));
     };
     const int nbatch = ntiles * NB;
     float4 xa[PB], xb[PB];
@@ -621,23 +620,19 @@ pair_h3_kernel(const __grid_constant__ PairArgs a, const __grid_constant__ Geo g
         tmem_ld16(acc1 + lane_addr + (uint32_t)ch0, r);
         tmem_wait16(r);
         float x[16];
-        if (pix_mid >= 0) {
-          if (has_mask) {
+        const bool in_mid = pix_mid >= 0;          // rows outside the image feed zero padding to the second conv
+        if (has_mask) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) x[i] = mk[i] > 0.f ? __uint_as_float(r[i]) : 0.f;
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-              const float4 bb = *reinterpret_cast<const float4*>(b1s + ch0 + i);
-              x[i] = fmaxf(__uint_as_float(r[i]) + bb.x, 0.f);
-              x[i + 1] = fmaxf(__uint_as_float(r[i + 1]) + bb.y, 0.f);
-              x[i + 2] = fmaxf(__uint_as_float(r[i + 2]) + bb.z, 0.f);
-              x[i + 3] = fmaxf(__uint_as_float(r[i + 3]) + bb.w, 0.f);
-            }
-          }
+          for (int i = 0; i < 16; ++i) x[i] = (in_mid && mk[i] > 0.f) ? __uint_as_float(r[i]) : 0.f;
         } else {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) x[i] = 0.f;
+          for (int i = 0; i < 16; i += 4) {
+            const float4 bb = *reinterpret_cast<const float4*>(b1s + ch0 + i);
+            x[i] = in_mid ? fmaxf(__uint_as_float(r[i]) + bb.x, 0.f) : 0.f;
+            x[i + 1] = in_mid ? fmaxf(__uint_as_float(r[i + 1]) + bb.y, 0.f) : 0.f;
+            x[i + 2] = in_mid ? fmaxf(__uint_as_float(r[i + 2]) + bb.z, 0.f) : 0.f;
+            x[i + 3] = in_mid ? fmaxf(__uint_as_float(r[i + 3]) + bb.w, 0.f) : 0.f;
+          }
         }
         if (has_mask && pc + 1 < NPIECE && mid_row != nullptr) { ldg8(mid_row + (pc + 1) * 16, &mk[0]); ldg8(mid_row + (pc + 1) * 16 + 8, &mk[8]); }
         if (mid_dst != nullptr) {

@@ -611,6 +611,21 @@ pair_h3_kernel(const __grid_constant__ PairArgs a, const __grid_constant__ Geo g
         for (int i = 0; i < 16; ++i) mk[i] = 0.f;
         if (mid_row != nullptr) { ldg8(mid_row, &mk[0]); ldg8(mid_row + 8, &mk[8]); }
       }
+      if (a.epi != kEpiFwd) {
+        // the rows epilogue 2 of this tile will read (p / dy, y / block input): pull them into L2 now, one epilogue
+        // earlier -- its register prefetch runs only one 16-column piece ahead, which covers an L2 hit, not DRAM
+        const long pix_out = row_pixel(ti, true);
+        if (pix_out >= 0) {
+          const float* e0p = a.e0 + img + (size_t)pix_out * C + chw;
+#pragma unroll
+          for (int l = 0; l < C / 64; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(e0p + l * 32));
+          if (a.epi == kEpiBwdResidual) {
+            const float* e1p = a.e1 + img + (size_t)pix_out * C + chw;
+#pragma unroll
+            for (int l = 0; l < C / 64; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(e1p + l * 32));
+          }
+        }
+      }
       { H3_T0(); mbar_wait(hdr + OFF_ACC1FULL + 8 * ab, (uint32_t)(ause & 1)); H3_T1(0); }
       tc_fence_after();
 #pragma unroll 1

@@ -492,6 +492,14 @@ pair_h3_kernel(const __grid_constant__ PairArgs a, const __grid_constant__ Geo g
           if (cidx < geo.dd && ul >= 0 && vl >= 0 && u < geo.U && v < geo.V) pix = a.vert_first ? u * a.W + v : v * a.W + u;
         }
         pixtab[(t & 1) * IN_MAX_ALL + lt] = pix;
+        if (a.mid_mask != nullptr && pix >= 0) {
+          // backward launches: the saved activation whose sign masks `mid` is read by epilogue 1 of this tile, about one
+          // tile from now, one 16-column piece ahead of its use: pull the pixel's row into L2 already (the mid pixels are
+          // the input pixels minus the halo along the first conv's axis)
+          const float* mrow_p = a.mid_mask + (size_t)ti.n * a.H * a.W * C + (size_t)pix * C;
+#pragma unroll
+          for (int l = 0; l < C / 32; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(mrow_p + l * 32));
+        }
       }
       { H3_T0(); named_bar_sync(2, N_LOAD); H3_T1(3); }
       src = a.in + (size_t)ti.n * a.H * a.W * C + c4 * 4;      // + 32 * chunk at issue time

@@ -12,9 +12,9 @@ Parity pin: the reference has no tests or golden vectors of its own
 therefore pinned against OUTPUTS OF THE REFERENCE ITSELF, run in the build
 container: ``tests/golden/make_golden.py`` imports ``/root/reference`` and
 writes the committed fixtures under ``tests/golden/``;
-``tests/test_oracle_golden.py`` checks this file against them, and
-``tests/test_oracle_vs_reference.py`` checks it live against the imported
-reference whenever ``/root/reference`` exists.
+``tests/test_oracle_golden.py`` checks this file against them (the generating
+scripts ``tests/golden/make_golden*.py`` are the live comparison with the
+imported reference; they run wherever ``/root/reference`` exists).
 
 Every function cites the reference lines it follows (paths relative to the
 reference repo root).  Tensors are NCHW fp32, labels int64, exactly as the

@@ -149,6 +149,18 @@ static bool use_tc_wgrad(int C) {
   }();
   return mode == 1 && (C == 64 || C == 128);
 }
+// "S16" format of the backward gradient workspaces (T1 = ds / dp, T2 = dc' / da'): a plane of bf16 hi halves followed by
+// a plane of bf16 lo halves (x = hi + lo; the bytes of the fp32 tensor).  Their producers (bn_bwd_apply, the backward
+// pair's first epilogue) have the halves at hand or split once; their consumers (the backward pair's loader, the weight-
+// gradient producers) copy operand words instead of converting.  Only when every consumer is a tensor-core kernel;
+// MDIL_S16=0 keeps fp32 workspaces for A/B measurements.
+static bool s16_enabled() {
+  static const int on = [] {
+    const char* e = getenv("MDIL_S16");
+    return (e != nullptr && strcmp(e, "0") == 0) ? 0 : 1;
+  }();
+  return on == 1 && pair_impl_mode() == 4;
+}
 static inline const float* tc_stream(const float* packed, int C, int which) {
   if (!use_tensor_cores(C)) return nullptr;
   // tc3: four streams of 14 C^2 floats (hi/lo TF32 images); h3: four streams of 14 C^2 16-bit values (= 7 C^2 floats)
@@ -316,7 +328,7 @@ static int flush_wgrad_jobs(WgradJobList* jl, cudaStream_t s) {
 }
 
 static int nb1d_wgrad(const mdil_nb1d_desc* d, int dil, bool vert, int taps, const float* A, const float* sc,
-                      const float* sh, const float* G, float* dW, float* db, float* acc_scratch, float* db_scratch,
+                      const float* sh, const float* G, int g_split, float* dW, float* db, float* acc_scratch, float* db_scratch,
                       UnpackList* ul, WgradJobList* jl, cudaStream_t s) {
   const int C = d->C;
   if (dW == nullptr) {
@@ -329,13 +341,14 @@ static int nb1d_wgrad(const mdil_nb1d_desc* d, int dil, bool vert, int taps, con
     WgradTcArgs w;
     memset(&w, 0, sizeof(w));
     w.A = A; w.a_scale = sc; w.a_shift = sh; w.G = G; w.dWacc = acc_scratch; w.db = db != nullptr ? db_scratch : nullptr;
-    w.N = d->N; w.H = d->H; w.W = d->W; w.C = C; w.dil = dil; w.ntaps = taps; w.vert = vert ? 1 : 0;
+    w.N = d->N; w.H = d->H; w.W = d->W; w.C = C; w.dil = dil; w.ntaps = taps; w.vert = vert ? 1 : 0; w.g_split = g_split;
     jl->job[jl->n++] = w;        // launched together with the pair's other weight gradients (flush_wgrad_jobs)
     UnpackItem& it = ul->item[ul->n++];
     it.acc = acc_scratch; it.dW = dW; it.ntaps = taps; it.s_ci = s_ci; it.s_co = s_co; it.s_t = s_t;
     it.dbacc = db_scratch; it.db = db;
     return 0;
   }
+  MDIL_REQUIRE(!g_split, "nb1d_bwd: S16 gradients need the tensor-core weight-gradient kernel");
   MDIL_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)C * C * taps, s));
   ConvGeom g = taps == 1 ? pointwise_geom(d->N, d->H, d->W, C) : taps3_geom(d->N, d->H, d->W, C, dil, vert);
   return launch_wgrad_taps(g, A, sc, sh, G, dW, s_ci, s_co, s_t, db, s);
@@ -343,7 +356,7 @@ static int nb1d_wgrad(const mdil_nb1d_desc* d, int dil, bool vert, int taps, con
 
 // one weight gradient of the packed-4 view through wgrad_tc<64>; its [3][64][64] accumulator is folded back by `ul`
 static int nb1d_wgrad_p4(const mdil_nb1d_desc* d, bool vert, const float* A, const float* sc, const float* sh, const float* G,
-                         float* dW, float* db, float* acc, float* bacc, UnpackP4List* ul, WgradJobList* jl) {
+                         int g_split, float* dW, float* db, float* acc, float* bacc, UnpackP4List* ul, WgradJobList* jl) {
   if (dW == nullptr) {
     MDIL_REQUIRE(db == nullptr, "nb1d_bwd: bias gradient without weight gradient is not supported");
     return 0;
@@ -351,7 +364,7 @@ static int nb1d_wgrad_p4(const mdil_nb1d_desc* d, bool vert, const float* A, con
   WgradTcArgs w;
   memset(&w, 0, sizeof(w));
   w.A = A; w.a_scale = sc; w.a_shift = sh; w.G = G; w.dWacc = acc; w.db = db != nullptr ? bacc : nullptr;
-  w.N = d->N; w.H = d->H; w.W = d->W / 4; w.C = 64; w.dil = 1; w.ntaps = 3; w.vert = vert ? 1 : 0;
+  w.N = d->N; w.H = d->H; w.W = d->W / 4; w.C = 64; w.dil = 1; w.ntaps = 3; w.vert = vert ? 1 : 0; w.g_split = g_split;
   jl->job[jl->n++] = w;
   UnpackP4Item& it = ul->item[ul->n++];
   it.acc = acc; it.dW = dW; it.dbacc = bacc; it.db = db; it.horizontal = vert ? 0 : 1;
@@ -388,31 +401,33 @@ static int nb1d_bwd_p4(const mdil_nb1d_desc* d, const float* dy, const float* x,
   // ---- BN2 backward (+ ReLU mask of y, dropout): ds  (elementwise kernels on the 16-channel view)
   MDIL_TRY(launch_bn_bwd_stats(dy, y, drop_mask, sv->s, st2, sums2, N, HW, C, s));
   MDIL_TRY(launch_bn_bwd_finalize(sums2, count, C, w->bn2.weight, st2, coef2, gr->bn2_w, gr->bn2_b, s));
-  MDIL_TRY(launch_bn_bwd_apply(dy, y, drop_mask, sv->s, st2, coef2, T1, N, HW, C, s));
+  const int s16 = s16_enabled() ? 1 : 0;
+  MDIL_TRY(launch_bn_bwd_apply(dy, y, drop_mask, sv->s, st2, coef2, T1, N, HW, C, s, s16));
 
   // ---- pair 2 backward: ds -> dc' -> dq (masked by r>0), sums for BN1 backward
   PairArgs a;
   memset(&a, 0, sizeof(a));
+  a.in_split = s16; a.mid_out_split = s16;
   a.N = N; a.H = H; a.W = W / 4; a.C = CP; a.has_adapter = 0; a.vert_first = 0; a.dil = 1; a.view_c = C;
   a.in = T1; a.wstream_tc = p4_stream(packed, 2); a.mid_mask = sv->c; a.mid_out = T2; a.out = T3;
   a.epi = kEpiBwdMaskStats; a.e0 = sv->p; a.e_stats = rep1; a.sums = sums1;
   MDIL_TRY(launch_pair(a, s));
   WgradJobList jl;
   jl.n = 0;
-  MDIL_TRY(nb1d_wgrad_p4(d, false, sv->c, nullptr, nullptr, T1, gr->w13_2, gr->b13_2, wacc + 0 * WS, bacc + 0 * CP, &ul, &jl));
-  MDIL_TRY(nb1d_wgrad_p4(d, true, sv->p, rep1 + 2 * CP, rep1 + 3 * CP, T2, gr->w31_2, gr->b31_2, wacc + 1 * WS, bacc + 1 * CP, &ul, &jl));
+  MDIL_TRY(nb1d_wgrad_p4(d, false, sv->c, nullptr, nullptr, T1, s16, gr->w13_2, gr->b13_2, wacc + 0 * WS, bacc + 0 * CP, &ul, &jl));
+  MDIL_TRY(nb1d_wgrad_p4(d, true, sv->p, rep1 + 2 * CP, rep1 + 3 * CP, T2, s16, gr->w31_2, gr->b31_2, wacc + 1 * WS, bacc + 1 * CP, &ul, &jl));
   MDIL_TRY(flush_wgrad_jobs(&jl, s));
 
   // ---- BN1 backward: dq -> dp (overwrites ds)
   MDIL_TRY(launch_bn_bwd_finalize(sums1, count, C, w->bn1.weight, st1, coef1, gr->bn1_w, gr->bn1_b, s, 4));
-  MDIL_TRY(launch_bn_bwd_apply(T3, nullptr, nullptr, sv->p, st1, coef1, T1, N, HW, C, s));
+  MDIL_TRY(launch_bn_bwd_apply(T3, nullptr, nullptr, sv->p, st1, coef1, T1, N, HW, C, s, s16));
 
   // ---- pair 1 backward: dp -> da' -> dx (+ residual dy * (y>0))
   a.in = T1; a.wstream_tc = p4_stream(packed, 3); a.mid_mask = sv->a; a.mid_out = T2; a.out = dx;
   a.epi = kEpiBwdResidual; a.e0 = dy; a.e1 = y; a.e_stats = nullptr; a.sums = nullptr;
   MDIL_TRY(launch_pair(a, s));
-  MDIL_TRY(nb1d_wgrad_p4(d, false, sv->a, nullptr, nullptr, T1, gr->w13_1, gr->b13_1, wacc + 2 * WS, bacc + 2 * CP, &ul, &jl));
-  MDIL_TRY(nb1d_wgrad_p4(d, true, x, nullptr, nullptr, T2, gr->w31_1, gr->b31_1, wacc + 3 * WS, bacc + 3 * CP, &ul, &jl));
+  MDIL_TRY(nb1d_wgrad_p4(d, false, sv->a, nullptr, nullptr, T1, s16, gr->w13_1, gr->b13_1, wacc + 2 * WS, bacc + 2 * CP, &ul, &jl));
+  MDIL_TRY(nb1d_wgrad_p4(d, true, x, nullptr, nullptr, T2, s16, gr->w31_1, gr->b31_1, wacc + 3 * WS, bacc + 3 * CP, &ul, &jl));
   MDIL_TRY(flush_wgrad_jobs(&jl, s));
   return launch_wgrad_unpack_p4(ul, s);
 }
@@ -453,13 +468,15 @@ int mdil_nb1d_bwd(const mdil_nb1d_desc* d, const float* dy, const float* x, cons
   // ---- BN2 backward (+ ReLU mask of y, dropout): ds
   MDIL_TRY(launch_bn_bwd_stats(dy, y, drop_mask, sv->s, st2, sums2, N, HW, C, s));
   MDIL_TRY(launch_bn_bwd_finalize(sums2, count, C, w->bn2.weight, st2, coef2, gr->bn2_w, gr->bn2_b, s));
-  MDIL_TRY(launch_bn_bwd_apply(dy, y, drop_mask, sv->s, st2, coef2, T1, N, HW, C, s));
+  const int s16 = (s16_enabled() && use_tensor_cores(C) && use_tc_wgrad(C)) ? 1 : 0;
+  MDIL_TRY(launch_bn_bwd_apply(dy, y, drop_mask, sv->s, st2, coef2, T1, N, HW, C, s, s16));
   static const int stop = [] { const char* dbg = getenv("MDIL_DEBUG_STOP"); return dbg ? atoi(dbg) : 0; }();   // tools/debug_nb1d.py
   if (stop == 1) return 0;
 
   // ---- pair 2 backward: ds -> dc' -> dq (masked by r>0), sums for BN1 backward
   PairArgs a;
   memset(&a, 0, sizeof(a));
+  a.in_split = s16; a.mid_out_split = s16;
   a.N = N; a.H = H; a.W = W; a.C = C; a.has_adapter = d->has_adapter; a.vert_first = 0;
   a.in = T1; a.wstream = packed + 14 * CC; a.wstream_tc = tc_stream(packed, C, 2); a.mid_mask = sv->c; a.mid_out = T2; a.out = T3;
   a.epi = kEpiBwdMaskStats; a.e0 = sv->p; a.e_stats = st1; a.sums = sums1; a.dil = d->dil;
@@ -469,16 +486,16 @@ int mdil_nb1d_bwd(const mdil_nb1d_desc* d, const float* dy, const float* x, cons
   // ---- weight gradients of pair 2
   WgradJobList jl;
   jl.n = 0;
-  MDIL_TRY(nb1d_wgrad(d, d->dil, false, 3, sv->c, nullptr, nullptr, T1, gr->w13_2, gr->b13_2, wacc + 0 * WS, bacc + 0 * C, &ul, &jl, s));
+  MDIL_TRY(nb1d_wgrad(d, d->dil, false, 3, sv->c, nullptr, nullptr, T1, s16, gr->w13_2, gr->b13_2, wacc + 0 * WS, bacc + 0 * C, &ul, &jl, s));
   if (d->has_adapter)
-    MDIL_TRY(nb1d_wgrad(d, 1, true, 1, sv->p, st1 + 2 * C, st1 + 3 * C, T1, gr->wp2, gr->bp2, wacc + 1 * WS, bacc + 1 * C, &ul, &jl, s));
-  MDIL_TRY(nb1d_wgrad(d, d->dil, true, 3, sv->p, st1 + 2 * C, st1 + 3 * C, T2, gr->w31_2, gr->b31_2, wacc + 2 * WS, bacc + 2 * C, &ul, &jl, s));
+    MDIL_TRY(nb1d_wgrad(d, 1, true, 1, sv->p, st1 + 2 * C, st1 + 3 * C, T1, s16, gr->wp2, gr->bp2, wacc + 1 * WS, bacc + 1 * C, &ul, &jl, s));
+  MDIL_TRY(nb1d_wgrad(d, d->dil, true, 3, sv->p, st1 + 2 * C, st1 + 3 * C, T2, s16, gr->w31_2, gr->b31_2, wacc + 2 * WS, bacc + 2 * C, &ul, &jl, s));
   MDIL_TRY(flush_wgrad_jobs(&jl, s));     // the pair's three weight gradients: one launch (T1 is overwritten below)
 
   if (stop == 3) return 0;
   // ---- BN1 backward: dq -> dp (overwrites ds)
   MDIL_TRY(launch_bn_bwd_finalize(sums1, count, C, w->bn1.weight, st1, coef1, gr->bn1_w, gr->bn1_b, s));
-  MDIL_TRY(launch_bn_bwd_apply(T3, nullptr, nullptr, sv->p, st1, coef1, T1, N, HW, C, s));
+  MDIL_TRY(launch_bn_bwd_apply(T3, nullptr, nullptr, sv->p, st1, coef1, T1, N, HW, C, s, s16));
 
   // ---- pair 1 backward: dp -> da' -> dx (+ residual dy * (y>0))
   a.in = T1; a.wstream = packed + 21 * CC; a.wstream_tc = tc_stream(packed, C, 3); a.mid_mask = sv->a; a.mid_out = T2; a.out = dx;
@@ -486,9 +503,9 @@ int mdil_nb1d_bwd(const mdil_nb1d_desc* d, const float* dy, const float* x, cons
   MDIL_TRY(launch_pair(a, s));
 
   // ---- weight gradients of pair 1
-  MDIL_TRY(nb1d_wgrad(d, 1, false, 3, sv->a, nullptr, nullptr, T1, gr->w13_1, gr->b13_1, wacc + 3 * WS, bacc + 3 * C, &ul, &jl, s));
-  if (d->has_adapter) MDIL_TRY(nb1d_wgrad(d, 1, true, 1, x, nullptr, nullptr, T1, gr->wp1, gr->bp1, wacc + 4 * WS, bacc + 4 * C, &ul, &jl, s));
-  MDIL_TRY(nb1d_wgrad(d, 1, true, 3, x, nullptr, nullptr, T2, gr->w31_1, gr->b31_1, wacc + 5 * WS, bacc + 5 * C, &ul, &jl, s));
+  MDIL_TRY(nb1d_wgrad(d, 1, false, 3, sv->a, nullptr, nullptr, T1, s16, gr->w13_1, gr->b13_1, wacc + 3 * WS, bacc + 3 * C, &ul, &jl, s));
+  if (d->has_adapter) MDIL_TRY(nb1d_wgrad(d, 1, true, 1, x, nullptr, nullptr, T1, s16, gr->wp1, gr->bp1, wacc + 4 * WS, bacc + 4 * C, &ul, &jl, s));
+  MDIL_TRY(nb1d_wgrad(d, 1, true, 3, x, nullptr, nullptr, T2, s16, gr->w31_1, gr->b31_1, wacc + 5 * WS, bacc + 5 * C, &ul, &jl, s));
   MDIL_TRY(flush_wgrad_jobs(&jl, s));
   return launch_wgrad_unpack_multi(ul, C, s);
 }

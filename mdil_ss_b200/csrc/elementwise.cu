@@ -234,10 +234,16 @@ int launch_bn_bwd_finalize(const double* sums, double count, int C, const float*
   return 0;
 }
 
+__device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+  const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(x1 - h1), "f"(x0 - h0));
+}
+
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ drop,
                     const float* __restrict__ u, const float* __restrict__ stats, const float* __restrict__ coef,
-                    float* __restrict__ du, size_t total4, size_t HWC4, int C) {
+                    float* __restrict__ du, size_t total4, size_t HWC4, int C, int split) {
   const int C4 = C >> 2;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
     int c4 = (int)(i % C4);
@@ -259,15 +265,25 @@ bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ y, c
     o.y = g.y * (v.y - k1.y - (uu.y - mean.y) * istd.y * k2.y);
     o.z = g.z * (v.z - k1.z - (uu.z - mean.z) * istd.z * k2.z);
     o.w = g.w * (v.w - k1.w - (uu.w - mean.w) * istd.w * k2.w);
-    reinterpret_cast<float4*>(du)[i] = o;
+    if (split) {
+      // "S16" internal format of the gradient tensors the tensor-core kernels consume: every group of four channels
+      // (16 bytes, where the fp32 values would be) holds its four bf16 hi halves, then its four bf16 lo halves
+      // (x = hi + lo) -- same addresses and access widths as fp32, but loaders / producers copy instead of converting
+      uint4 w;
+      split_bf16x2(o.x, o.y, w.x, w.z);
+      split_bf16x2(o.z, o.w, w.y, w.w);
+      reinterpret_cast<uint4*>(du)[i] = w;
+    } else {
+      reinterpret_cast<float4*>(du)[i] = o;
+    }
   }
 }
 
 int launch_bn_bwd_apply(const float* dy, const float* y, const float* drop, const float* u, const float* stats,
-                        const float* coef, float* du, int N, size_t HW, int C, cudaStream_t s) {
+                        const float* coef, float* du, int N, size_t HW, int C, cudaStream_t s, int split) {
   MDIL_REQUIRE(C % 4 == 0, "bn_bwd_apply: C % 4");
   size_t total4 = (size_t)N * HW * (C / 4);
-  bn_bwd_apply_kernel<<<ew_grid(total4, 256), 256, 0, s>>>(dy, y, drop, u, stats, coef, du, total4, HW * (C / 4), C);
+  bn_bwd_apply_kernel<<<ew_grid(total4, 256), 256, 0, s>>>(dy, y, drop, u, stats, coef, du, total4, HW * (C / 4), C, split);
   MDIL_LAUNCH_CHECK();
   return 0;
 }

@@ -32,8 +32,9 @@ int launch_bn_bwd_finalize(const double* sums, double count, int C, const float*
                            float* dgamma, float* dbeta, cudaStream_t s, int fold = 1);   // fold: sums are [2][fold*C]
 
 // du = coef0 * (dz - coef1 - uhat*coef2)
+// split != 0: du is written in the "S16" format (per group of 4 channels = 16 bytes: 4 bf16 hi halves, 4 bf16 lo halves; x = hi + lo)
 int launch_bn_bwd_apply(const float* dy, const float* y, const float* drop, const float* u, const float* stats,
-                        const float* coef, float* du, int N, size_t HW, int C, cudaStream_t s);
+                        const float* coef, float* du, int N, size_t HW, int C, cudaStream_t s, int split = 0);
 
 // max-pool 2x2 s2 of x[N,H,W,ldin] channels [0,Cin) -> u[N,H/2,W/2,ldu] channels [coff, coff+Cin)
 int launch_pool_fwd(const float* x, float* u, int N, int H, int W, int Cin, int ldin, int ldu, int coff, cudaStream_t s);
@@ -111,6 +112,8 @@ struct PairArgs {
   int N, H, W, C, dil, has_adapter, vert_first;
   int trace;               // debug: CTA 0 prints its phase timestamps (MDIL_TC_TRACE=1)
   int view_c;              // 0, or the logical channel count when the launch runs on a packed view (profiling kinds only)
+  int in_split;            // `in` is in the S16 format (per 4 channels: 4 bf16 hi, 4 bf16 lo halves): the loader copies (backward launches)
+  int mid_out_split;       // write `mid_out` in the S16 format (backward launches: the operand halves are stored as they are)
 };
 int launch_pair(const PairArgs& a, cudaStream_t s);          // dispatch: tensor-core kernel when wstream_tc != NULL
 int launch_pair_ffma(const PairArgs& a, cudaStream_t s);     // nb1d_pair.cu (FP32 FFMA; all C)
@@ -146,6 +149,7 @@ struct WgradTcArgs {
   float* db;               // nullable [C], zeroed by the caller
   int N, H, W, C, dil, ntaps, vert;
   int trace;               // debug: CTA 0 prints its wait counters (MDIL_TC_TRACE=1)
+  int g_split;             // G is in the S16 format (per 4 channels: 4 bf16 hi, 4 bf16 lo halves): the producers copy it
 };
 int launch_wgrad_tc(const WgradTcArgs& a, cudaStream_t s);
 // up to three independent jobs (same C) in ONE launch, CTAs split between them: one accumulator flush per CTA instead of three

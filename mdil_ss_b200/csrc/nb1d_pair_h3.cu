@@ -167,6 +167,10 @@ __device__ __forceinline__ void ldg8(const float* p, float* v) {
                : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p));
 }
 // 256-bit store of results nothing in this kernel reads back: volatile (must happen) but no memory clobber
+__device__ __forceinline__ void stg8u(void* p, const uint32_t* v) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+               "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
 __device__ __forceinline__ void stg8(float* p, const float* v) {
   asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
                "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]));
@@ -477,6 +481,7 @@ pair_h3_kernel(const __grid_constant__ PairArgs a, const __grid_constant__ Geo g
     TileIter ti;                                 // tile of the batch being ISSUED
     ti.init(geo);
     const float* src = nullptr;
+    const bool in_split = a.in_split != 0;       // S16 input: every 16 bytes hold 4 bf16 hi halves + 4 bf16 lo halves
     // start of tile t on the issue side: pixel table of the tile (-1: outside the image = zero padding) + source pointer.
     // The table is double-buffered by t & 1: a thread writing table t+2 has passed the barrier of tile t+1, which every
     // thread reaches only after its last read of table t.
@@ -516,7 +521,7 @@ pair_h3_kernel(const __grid_constant__ PairArgs a, const __grid_constant__ Geo g
         if (row < IN_MAX) {
           const int pix = ptab[row];
           if (pix >= 0) {
-            x[p] = ldg4(src + (size_t)pix * C + bt * KCH);
+            x[p] = ldg4(src + (size_t)pix * C + bt * KCH);    // S16 input: the same 16 bytes hold 4 hi + 4 lo halves
             valid |= 1u << p;
           }
         }
@@ -542,8 +547,13 @@ pair_h3_kernel(const __grid_constant__ PairArgs a, const __grid_constant__ Geo g
           v4.w = ok ? fmaxf(fmaf(v4.w, sc.w, sh.w), 0.f) : 0.f;
         }
         uint2 hi, lo;
-        split2<FMT>(v4.x, v4.y, hi.x, lo.x);
-        split2<FMT>(v4.z, v4.w, hi.y, lo.y);
+        if (in_split) {
+          hi = make_uint2(__float_as_uint(v4.x), __float_as_uint(v4.y));
+          lo = make_uint2(__float_as_uint(v4.z), __float_as_uint(v4.w));
+        } else {
+          split2<FMT>(v4.x, v4.y, hi.x, lo.x);
+          split2<FMT>(v4.z, v4.w, hi.y, lo.y);
+        }
         const uint32_t off = (uint32_t)row * 128u + (((chunk16 ^ ((uint32_t)row & 7u)) << 4) | half8);
         if (row < geo.INROWS) {
           *reinterpret_cast<uint2*>(buf + off) = hi;
@@ -581,6 +591,7 @@ pair_h3_kernel(const __grid_constant__ PairArgs a, const __grid_constant__ Geo g
     for (int i = 0; i < NPIECE; ++i) { run1[i] = 0.f; run2[i] = 0.f; }
     const uint32_t sw = (uint32_t)m & 7u;
     const bool has_mask = a.mid_mask != nullptr;
+    const bool mid_split = a.mid_out != nullptr && a.mid_out_split != 0;
 
     // pixel of accumulator row m in tile `ti`: the `mid` pixel (second-conv input, halo included) or the output pixel
     auto row_pixel = [&](const TileIter& ti, bool out) -> long {
@@ -658,7 +669,7 @@ pair_h3_kernel(const __grid_constant__ PairArgs a, const __grid_constant__ Geo g
           }
         }
         if (has_mask && pc + 1 < NPIECE && mid_row != nullptr) { ldg8(mid_row + (pc + 1) * 16, &mk[0]); ldg8(mid_row + (pc + 1) * 16 + 8, &mk[8]); }
-        if (mid_dst != nullptr) {
+        if (mid_dst != nullptr && !mid_split) {
           stg8(mid_dst + pc * 16, &x[0]);
           stg8(mid_dst + pc * 16 + 8, &x[8]);
         }
@@ -666,6 +677,12 @@ pair_h3_kernel(const __grid_constant__ PairArgs a, const __grid_constant__ Geo g
           uint32_t hi[8], lo[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) split2<FMT>(x[2 * i], x[2 * i + 1], hi[i], lo[i]);
+          if (mid_split && mid_dst != nullptr) {      // S16 `mid_out`: per 4 channels, the 2 hi words then the 2 lo words
+            const uint32_t w0[8] = {hi[0], hi[1], lo[0], lo[1], hi[2], hi[3], lo[2], lo[3]};
+            const uint32_t w1[8] = {hi[4], hi[5], lo[4], lo[5], hi[6], hi[7], lo[6], lo[7]};
+            stg8u(mid_dst + pc * 16, w0);
+            stg8u(mid_dst + pc * 16 + 8, w1);
+          }
           unsigned char* rowp = buf + (size_t)(ch0 >> 6) * K::SLAB_BYTES + (size_t)m * 128;
           const uint32_t c16 = (uint32_t)(ch0 & 63) >> 3;       // first of the two 16-byte chunks of this piece
           const uint32_t o0 = ((c16 ^ sw) << 4), o1 = (((c16 + 1) ^ sw) << 4);
@@ -1070,6 +1087,8 @@ int launch_pack_block_p4(const float* const* w4, const float* const* b4, void* p
 int launch_pair_h3(const PairArgs& a, cudaStream_t s) {
   const int ov = h3_fmt_override();
   const int fmt = ov >= 0 ? ov : ((a.epi == kEpiFwd || a.epi == kEpiFwdBnRes) ? 0 : 1);   // forward: fp16 halves, backward: bf16
+  MDIL_REQUIRE(!(a.in_split || a.mid_out_split) || (fmt == 1 && a.in_scale == nullptr),
+               "pair_h3: S16 tensors hold bf16 halves (backward launches, no input prologue)");
   if (a.trace) {
     if (a.C == 128) return fmt == 0 ? h3::launch_c<128, 0, true>(a, s) : h3::launch_c<128, 1, true>(a, s);
     if (a.C == 64) return fmt == 0 ? h3::launch_c<64, 0, true>(a, s) : h3::launch_c<64, 1, true>(a, s);

@@ -286,6 +286,7 @@ wgrad_tc_kernel(const __grid_constant__ Jobs jobs) {
       }
     };
     // register double buffer: the loads of batch n+1 are issued before batch n is split and stored
+    const bool g_split = a.g_split != 0;
     auto load_batch = [&](FillDesc (&fd)[B], float4 (&av)[B][RPT], float4 (&gv)[B][RPT], uint32_t& inside) {
       inside = 0;   // bit b*RPT+i: the pixel is inside the image (BN+ReLU prologue applies)
 #pragma unroll
@@ -301,7 +302,7 @@ wgrad_tc_kernel(const __grid_constant__ Jobs jobs) {
             if (fd[b].uok && v < pl.V) {
               const size_t off = fd[b].img + fd[b].u * su + v * sv + ch;
               av[b][i] = ldg4(a.A + off);
-              if (fd[b].interior) gv[b][i] = ldg4(a.G + off);
+              if (fd[b].interior) gv[b][i] = ldg4(a.G + off);   // S16: the same 16 bytes hold 4 hi + 4 lo halves
               inside |= 1u << (b * RPT + i);
             }
           }
@@ -333,10 +334,21 @@ wgrad_tc_kernel(const __grid_constant__ Jobs jobs) {
           split4(a4, hi, lo);
           *reinterpret_cast<uint2*>(gen + (ad - hdr)) = hi;
           *reinterpret_cast<uint2*>(gen + (ad - hdr) + K::PART) = lo;
-          split4(g4, hi, lo);
+          if (g_split) {
+            hi = make_uint2(__float_as_uint(g4.x), __float_as_uint(g4.y));
+            lo = make_uint2(__float_as_uint(g4.z), __float_as_uint(g4.w));
+            if (a.db != nullptr) {
+              bsum.x += __uint_as_float(hi.x << 16) + __uint_as_float(lo.x << 16);
+              bsum.y += __uint_as_float(hi.x & 0xffff0000u) + __uint_as_float(lo.x & 0xffff0000u);
+              bsum.z += __uint_as_float(hi.y << 16) + __uint_as_float(lo.y << 16);
+              bsum.w += __uint_as_float(hi.y & 0xffff0000u) + __uint_as_float(lo.y & 0xffff0000u);
+            }
+          } else {
+            split4(g4, hi, lo);
+            bsum.x += g4.x; bsum.y += g4.y; bsum.z += g4.z; bsum.w += g4.w;
+          }
           *reinterpret_cast<uint2*>(gen + (ad - hdr) + 2 * K::PART) = hi;
           *reinterpret_cast<uint2*>(gen + (ad - hdr) + 3 * K::PART) = lo;
-          bsum.x += g4.x; bsum.y += g4.y; bsum.z += g4.z; bsum.w += g4.w;
         }
         fence_proxy_async();
         mbar_arrive(bar_full + 8 * (qq % NST));

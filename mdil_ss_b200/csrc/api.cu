@@ -521,7 +521,8 @@ size_t mdil_down_packed_floats(const mdil_down_desc* d) {
 
 size_t mdil_down_workspace_bytes(const mdil_down_desc* d) {
   size_t du = align_up((size_t)d->N * (d->H / 2) * (d->W / 2) * d->Cout * sizeof(float), 256);
-  return du + (size_t)2 * d->Cout * sizeof(double) + (size_t)3 * d->Cout * sizeof(float) + 4 * 256;
+  return du + (size_t)2 * d->Cout * sizeof(double) + (size_t)3 * d->Cout * sizeof(float) + 4 * 256 +
+         align_up(wgrad_gather_scratch_floats() * sizeof(float), 256);
 }
 
 static int check_down(const mdil_down_desc* d) {
@@ -601,9 +602,13 @@ int mdil_down_bwd(const mdil_down_desc* d, const float* dy, const float* x, cons
     g.GH = OH; g.GW = OW; g.ldg = Cout; g.g_coff = 0; g.g_sy = 1; g.g_sx = 1;
     g.CIN = down_cinp(d); g.COUT = Cc; g.COUT_PAD = down_coutp(d); g.CIN_VALID = Cin;
     fill_3x3_taps(g);
-    MDIL_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cc * Cin * 9, s));
-    if (db != nullptr) MDIL_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * Cc, s));
-    MDIL_TRY(launch_wgrad_taps(g, x, nullptr, nullptr, du, dw, 9, 9L * Cin, 1, db, s));  // [co][ci][3][3]
+    if (wgrad_gather_ok(g)) {     // 64 -> 128: nine gathered one-tap jobs on the tensor-core kernel
+      MDIL_TRY(launch_wgrad_gather_tc(g, x, du, dw, 9, 9L * Cin, 1, db, cv.take<float>(wgrad_gather_scratch_floats()), s));
+    } else {
+      MDIL_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cc * Cin * 9, s));
+      if (db != nullptr) MDIL_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * Cc, s));
+      MDIL_TRY(launch_wgrad_taps(g, x, nullptr, nullptr, du, dw, 9, 9L * Cin, 1, db, s));  // [co][ci][3][3]
+    }
   } else {
     MDIL_REQUIRE(db == nullptr, "down_bwd: bias gradient without weight gradient is not supported");
   }
@@ -627,7 +632,8 @@ size_t mdil_up_packed_floats(const mdil_up_desc* d) { return (size_t)18 * d->Cin
 
 size_t mdil_up_workspace_bytes(const mdil_up_desc* d) {
   size_t du = align_up((size_t)d->N * (2 * d->H) * (2 * d->W) * d->Cout * sizeof(float), 256);
-  return du + (size_t)2 * d->Cout * sizeof(double) + (size_t)3 * d->Cout * sizeof(float) + 4 * 256;
+  return du + (size_t)2 * d->Cout * sizeof(double) + (size_t)3 * d->Cout * sizeof(float) + 4 * 256 +
+         align_up(wgrad_gather_scratch_floats() * sizeof(float), 256);
 }
 
 static int check_up(const mdil_up_desc* d) {
@@ -690,9 +696,13 @@ int mdil_up_bwd(const mdil_up_desc* d, const float* dy, const float* x, const fl
   MDIL_TRY(launch_bn_bwd_apply(dy, y, nullptr, u, stats, coef, du, d->N, OHW, Cout, s));
   if (dw != nullptr) {
     ConvGeom g = up_parity_geom(d);
-    MDIL_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cin * Cout * 9, s));
-    if (db != nullptr) MDIL_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * Cout, s));
-    MDIL_TRY(launch_wgrad_taps(g, x, nullptr, nullptr, du, dw, 9L * Cout, 9, 1, db, s));  // [ci][co][3][3]
+    if (wgrad_gather_ok(g)) {     // 128 -> 64, 64 -> 16: gathered one-tap jobs on the tensor-core kernel
+      MDIL_TRY(launch_wgrad_gather_tc(g, x, du, dw, 9L * Cout, 9, 1, db, cv.take<float>(wgrad_gather_scratch_floats()), s));
+    } else {
+      MDIL_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cin * Cout * 9, s));
+      if (db != nullptr) MDIL_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * Cout, s));
+      MDIL_TRY(launch_wgrad_taps(g, x, nullptr, nullptr, du, dw, 9L * Cout, 9, 1, db, s));  // [ci][co][3][3]
+    }
   } else {
     MDIL_REQUIRE(db == nullptr, "up_bwd: bias gradient without weight gradient is not supported");
   }

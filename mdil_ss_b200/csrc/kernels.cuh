@@ -150,10 +150,23 @@ struct WgradTcArgs {
   int N, H, W, C, dil, ntaps, vert;
   int trace;               // debug: CTA 0 prints its wait counters (MDIL_TC_TRACE=1)
   int g_split;             // G is in the S16 format (per 4 channels: 4 bf16 hi, 4 bf16 lo halves): the producers copy it
+  // gathered one-tap job (the strided 3x3 / transposed 3x3 convolutions of the samplers; launch_wgrad_gather_tc): the
+  // walk is over the virtual grid N x H x W of ConvGeom, activation pixel = (y*a_sy + a_dy, x*a_sx + a_dx) of an
+  // [AH, AW, lda] tensor (channels a_coff..a_coff+63), gradient pixel = (y*g_sy + g_dy, x*g_sx + g_dx) of [GH, GW, ldg]
+  // (channels g_coff..g_coff+g_cout-1); pixels outside their tensor contribute zeros
+  int AH, AW, lda, a_coff, a_sy, a_sx, a_dy, a_dx;
+  int GH, GW, ldg, g_coff, g_sy, g_sx, g_dy, g_dx, g_cout;
 };
 int launch_wgrad_tc(const WgradTcArgs& a, cudaStream_t s);
 // up to three independent jobs (same C) in ONE launch, CTAs split between them: one accumulator flush per CTA instead of three
 int launch_wgrad_tc_multi(const WgradTcArgs* a, int n, cudaStream_t s);
+// weight gradient of a tap-class convolution (ConvGeom: the samplers' strided / transposed 3x3) on the tensor-core kernel:
+// one gathered one-tap C = 64 job per (tap, 64-channel block of CIN), all in ONE launch.  Same contract as
+// launch_wgrad_taps, except that dW / db are overwritten (no zeroing by the caller); scratch: wgrad_gather_scratch_floats()
+bool wgrad_gather_ok(const ConvGeom& g);
+size_t wgrad_gather_scratch_floats();
+int launch_wgrad_gather_tc(const ConvGeom& g, const float* A, const float* G, float* dW, long s_ci, long s_co, long s_t,
+                           float* db, float* scratch, cudaStream_t s);
 int launch_wgrad_unpack(const float* acc, float* dW, int C, int ntaps, long s_ci, long s_co, long s_t, cudaStream_t s);
 struct UnpackItem { const float* acc; float* dW; int ntaps; long s_ci, s_co, s_t; const float* dbacc; float* db; };
 struct UnpackList { int n; UnpackItem item[6]; };

@@ -118,11 +118,12 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 struct Plan {
   int U, V, Ul, Vl, vblocks, nseg, L, units, halo;   // halo = 1 for 3 taps
 };
-struct Jobs {
-  WgradTcArgs a[3];
-  Plan pl[3];
-  int cta0[4];       // first CTA of every job; unused jobs are empty ranges at the end
+template <int NJ> struct JobsT {
+  WgradTcArgs a[NJ];
+  Plan pl[NJ];
+  int cta0[NJ + 1];  // first CTA of every job; unused jobs are empty ranges at the end
 };
+constexpr int kGatherJobs = 18;   // gathered one-tap jobs per launch (9 taps x two 64-channel blocks of CIN = 128)
 
 // decode unit -> strip + segment
 struct Unit { int n, ru, rv, vb, ul0, Lu; };
@@ -139,14 +140,17 @@ __device__ __forceinline__ Unit decode_unit(int unit, const Plan& pl, int d) {
   return u;
 }
 
-template <int C>
+template <int C, int NJ>
 __global__ void __launch_bounds__(NWORK + 96, 1)
-wgrad_tc_kernel(const __grid_constant__ Jobs jobs) {
+wgrad_tc_kernel(const __grid_constant__ JobsT<NJ> jobs) {
   using K = Cfg<C>;
+  constexpr bool GEN = NJ > 3;       // gathered one-tap jobs (sampler convolutions)
   // up to three independent weight gradients (the three convolutions of a factorised pair) share one launch: CTAs
   // [cta0[j], cta0[j+1]) work on job j.  Every CTA ends with ONE accumulator flush (red.global.add of [ntaps][C][C]),
   // which at C = 128 costs as much as the main loop of a 148-CTA launch: three launches paid it three times.
-  const int job = (int)blockIdx.x >= jobs.cta0[2] ? 2 : ((int)blockIdx.x >= jobs.cta0[1] ? 1 : 0);
+  int job = 0;
+#pragma unroll
+  for (int j = 1; j < NJ; ++j) job += (int)blockIdx.x >= jobs.cta0[j] ? 1 : 0;
   const WgradTcArgs& a = jobs.a[job];
   const Plan& pl = jobs.pl[job];
   const int bid = (int)blockIdx.x - jobs.cta0[job], nbid = jobs.cta0[job + 1] - jobs.cta0[job];
@@ -255,7 +259,7 @@ wgrad_tc_kernel(const __grid_constant__ Jobs jobs) {
     // Fills are walked in batches of B per group: the B * 2 * RPT independent 128-bit loads of a batch are all in flight
     // before the first one is consumed (64 KB in flight per SM instead of 16 KB: the producers were latency-bound).
     constexpr int B = 1;
-    struct FillDesc { size_t img; int u, rv, vb; uint32_t q; bool uok, interior, valid; };
+    struct FillDesc { size_t img; int n, u, rv, vb; uint32_t q; bool uok, interior, valid; };
     int unit = bid, f = 0, nfill = 0;
     uint32_t q = 0;
     Unit un;
@@ -278,6 +282,7 @@ wgrad_tc_kernel(const __grid_constant__ Jobs jobs) {
           fd.uok = ul >= 0 && fd.u < pl.U;
           fd.rv = un.rv; fd.vb = un.vb;
           fd.img = (size_t)un.n * a.H * a.W * C;
+          fd.n = un.n;
           fd.q = q;
           fd.valid = true;
         }
@@ -299,7 +304,16 @@ wgrad_tc_kernel(const __grid_constant__ Jobs jobs) {
           if (fd[b].valid) {
             const int row = row0 + i * RSTEP;
             const int v = fd[b].rv + d * (fd[b].vb * TP + row);
-            if (fd[b].uok && v < pl.V) {
+            if (GEN) {
+              if (fd[b].uok && v < pl.V) {     // (u, v) = (row, column) of the virtual grid
+                const int ay = fd[b].u * a.a_sy + a.a_dy, ax = v * a.a_sx + a.a_dx;
+                if ((unsigned)ay < (unsigned)a.AH && (unsigned)ax < (unsigned)a.AW)
+                  av[b][i] = ldg4(a.A + ((size_t)(fd[b].n * a.AH + ay) * a.AW + ax) * a.lda + a.a_coff + ch);
+                const int gy = fd[b].u * a.g_sy + a.g_dy, gx = v * a.g_sx + a.g_dx;
+                if ((unsigned)gy < (unsigned)a.GH && (unsigned)gx < (unsigned)a.GW && ch < a.g_cout)
+                  gv[b][i] = ldg4(a.G + ((size_t)(fd[b].n * a.GH + gy) * a.GW + gx) * a.ldg + a.g_coff + ch);
+              }
+            } else if (fd[b].uok && v < pl.V) {
               const size_t off = fd[b].img + fd[b].u * su + v * sv + ch;
               av[b][i] = ldg4(a.A + off);
               if (fd[b].interior) gv[b][i] = ldg4(a.G + off);   // S16: the same 16 bytes hold 4 hi + 4 lo halves
@@ -532,7 +546,7 @@ int launch_c(const WgradTcArgs* a, int n, cudaStream_t s) {
   // scales with the tap count (measured at C = 128: flush of three taps ~ one main loop)
   double cost[3] = {0, 0, 0}, tot = 0;
   for (int j = 0; j < n; ++j) { cost[j] = 1.0 + (C == 128 ? 0.85 : 0.3) * a[j].ntaps / 3.0; tot += cost[j]; }
-  Jobs jobs;
+  JobsT<3> jobs;
   memset(&jobs, 0, sizeof(jobs));
   int used = 0;
   for (int j = 0; j < n; ++j) {
@@ -546,10 +560,47 @@ int launch_c(const WgradTcArgs* a, int n, cudaStream_t s) {
     used += share;
   }
   for (int j = n; j <= 3; ++j) jobs.cta0[j] = used;
-  MDIL_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM));
-  wgrad_tc_kernel<C><<<used, NWORK + 96, K::SMEM, s>>>(jobs);
+  MDIL_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<C, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM));
+  wgrad_tc_kernel<C, 3><<<used, NWORK + 96, K::SMEM, s>>>(jobs);
   MDIL_LAUNCH_CHECK();
   return 0;
+}
+
+// gathered one-tap jobs (C = 64): equal CTA shares (every job walks the same virtual grid)
+static int launch_gather(const WgradTcArgs* a, int n, cudaStream_t s) {
+  using K = Cfg<64>;
+  static_assert(sizeof(JobsT<kGatherJobs>) <= 4000, "wgrad_tc: kernel parameter space");
+  JobsT<kGatherJobs> jobs;
+  memset(&jobs, 0, sizeof(jobs));
+  int used = 0;
+  for (int j = 0; j < n; ++j) {
+    int share = (kNumSMs * (j + 1)) / n - (kNumSMs * j) / n;
+    if (share < 1) share = 1;
+    jobs.a[j] = a[j];
+    jobs.pl[j] = make_plan(a[j], share);
+    MDIL_REQUIRE(jobs.pl[j].units > 0, "wgrad_tc: unit count");
+    if (jobs.pl[j].units < share) share = jobs.pl[j].units;
+    jobs.cta0[j] = used;
+    used += share;
+  }
+  for (int j = n; j <= kGatherJobs; ++j) jobs.cta0[j] = used;
+  MDIL_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<64, kGatherJobs>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM));
+  wgrad_tc_kernel<64, kGatherJobs><<<used, NWORK + 96, K::SMEM, s>>>(jobs);
+  MDIL_LAUNCH_CHECK();
+  return 0;
+}
+
+// accumulators of the gathered jobs -> dW in the caller's layout; bias sums -> db
+struct GatherUnpack { int n, cin, cout; int widx[kGatherJobs], ci0[kGatherJobs]; };
+__global__ void wgrad_gather_unpack_kernel(const GatherUnpack gu, const float* __restrict__ acc, float* __restrict__ dW,
+                                           long s_ci, long s_co, long s_t, const float* __restrict__ dbacc,
+                                           float* __restrict__ db) {
+  const int total = gu.n * 64 * 64;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int j = e >> 12, ci = gu.ci0[j] + ((e >> 6) & 63), co = e & 63;
+    if (ci < gu.cin && co < gu.cout) dW[(long)gu.widx[j] * s_t + (long)ci * s_ci + (long)co * s_co] = acc[e];
+  }
+  if (db != nullptr && blockIdx.x == 0 && threadIdx.x < gu.cout) db[threadIdx.x] = dbacc[threadIdx.x];
 }
 
 }  // namespace wtc
@@ -574,6 +625,51 @@ int launch_wgrad_tc_multi(const WgradTcArgs* a_in, int n, cudaStream_t s) {
 }
 
 int launch_wgrad_tc(const WgradTcArgs& a, cudaStream_t s) { return launch_wgrad_tc_multi(&a, 1, s); }
+
+bool wgrad_gather_ok(const ConvGeom& g) {
+  static const bool on = [] { const char* e = getenv("MDIL_WGRAD_GATHER"); return !(e != nullptr && strcmp(e, "0") == 0); }();
+  int taps = 0;
+  for (int c = 0; c < g.nclasses; ++c) taps += g.cls[c].ntaps;
+  return on && g.CIN % 64 == 0 && g.CIN_VALID == g.CIN && g.COUT % 4 == 0 && g.COUT <= 64 &&
+         taps * (g.CIN / 64) <= wtc::kGatherJobs && g.lda % 4 == 0 && g.a_coff % 4 == 0 && g.ldg % 4 == 0 && g.g_coff % 4 == 0;
+}
+size_t wgrad_gather_scratch_floats() { return (size_t)wtc::kGatherJobs * 64 * 64 + 64; }
+
+int launch_wgrad_gather_tc(const ConvGeom& g, const float* A, const float* G, float* dW, long s_ci, long s_co, long s_t,
+                           float* db, float* scratch, cudaStream_t s) {
+  static const int trace = getenv("MDIL_TC_TRACE") != nullptr ? 1 : 0;
+  MDIL_REQUIRE(wgrad_gather_ok(g), "wgrad_gather: unsupported geometry");
+  MDIL_REQUIRE(scratch != nullptr && ((uintptr_t)scratch & 15) == 0, "wgrad_gather: scratch buffer");
+  WgradTcArgs jobs[wtc::kGatherJobs];
+  wtc::GatherUnpack gu;
+  memset(&gu, 0, sizeof(gu));
+  float* dbacc = scratch + (size_t)wtc::kGatherJobs * 64 * 64;
+  int n = 0;
+  for (int c = 0; c < g.nclasses; ++c)
+    for (int t = 0; t < g.cls[c].ntaps; ++t)
+      for (int cb = 0; cb < g.CIN / 64; ++cb) {
+        WgradTcArgs& w = jobs[n];
+        memset(&w, 0, sizeof(w));
+        w.A = A; w.G = G; w.dWacc = scratch + (size_t)n * 64 * 64;
+        w.db = (db != nullptr && t == 0 && cb == 0) ? dbacc : nullptr;     // every class walks its gradient pixels once
+        w.N = g.N; w.H = g.VH; w.W = g.VW; w.C = 64; w.dil = 1; w.ntaps = 1; w.vert = 1; w.trace = trace;
+        w.AH = g.AH; w.AW = g.AW; w.lda = g.lda; w.a_coff = g.a_coff + 64 * cb; w.a_sy = g.a_sy; w.a_sx = g.a_sx;
+        w.a_dy = g.cls[c].a_dy[t]; w.a_dx = g.cls[c].a_dx[t];
+        w.GH = g.GH; w.GW = g.GW; w.ldg = g.ldg; w.g_coff = g.g_coff; w.g_sy = g.g_sy; w.g_sx = g.g_sx;
+        w.g_dy = g.cls[c].o_dy; w.g_dx = g.cls[c].o_dx; w.g_cout = g.COUT;
+        gu.widx[n] = g.cls[c].widx[t]; gu.ci0[n] = 64 * cb;
+        ++n;
+      }
+  gu.n = n; gu.cin = g.CIN_VALID; gu.cout = g.COUT;
+  MDIL_CUDA(cudaMemsetAsync(scratch, 0, sizeof(float) * ((size_t)n * 64 * 64), s));
+  MDIL_CUDA(cudaMemsetAsync(dbacc, 0, sizeof(float) * 64, s));
+  MDIL_TRY(wtc::launch_gather(jobs, n, s));
+  int grid = (n * 64 * 64 + 255) / 256;
+  if (grid > kNumSMs) grid = kNumSMs;
+  wtc::wgrad_gather_unpack_kernel<<<grid, 256, 0, s>>>(gu, scratch, dW, s_ci, s_co, s_t, dbacc, db);
+  MDIL_LAUNCH_CHECK();
+  return 0;
+}
 
 int launch_wgrad_unpack_multi(const UnpackList& ul, int C, cudaStream_t s) {
   if (ul.n == 0) return 0;

@@ -150,18 +150,21 @@ struct WgradTcArgs {
   int N, H, W, C, dil, ntaps, vert;
   int trace;               // debug: CTA 0 prints its wait counters (MDIL_TC_TRACE=1)
   int g_split;             // G is in the S16 format (per 4 channels: 4 bf16 hi, 4 bf16 lo halves): the producers copy it
-  // gathered one-tap job (the strided 3x3 / transposed 3x3 convolutions of the samplers; launch_wgrad_gather_tc): the
-  // walk is over the virtual grid N x H x W of ConvGeom, activation pixel = (y*a_sy + a_dy, x*a_sx + a_dx) of an
-  // [AH, AW, lda] tensor (channels a_coff..a_coff+63), gradient pixel = (y*g_sy + g_dy, x*g_sx + g_dx) of [GH, GW, ldg]
-  // (channels g_coff..g_coff+g_cout-1); pixels outside their tensor contribute zeros
-  int AH, AW, lda, a_coff, a_sy, a_sx, a_dy, a_dx;
-  int GH, GW, ldg, g_coff, g_sy, g_sx, g_dy, g_dx, g_cout;
+  // gathered job (the strided 3x3 / transposed 3x3 convolutions of the samplers; launch_wgrad_gather_tc): the walk is
+  // over the virtual grid N x H x W of ConvGeom.  The 64 operand channels are `nslots` slots of `sw` channels; slot k of
+  // the activation operand holds channels a_coff..a_coff+a_sw-1 of pixel (y*a_sy + dy_k, x*a_sx + dx_k) of an
+  // [AH, AW, lda] tensor, slot k of the gradient operand channels g_coff.. of pixel (y*g_sy + dy_k, x*g_sx + dx_k) of
+  // [GH, GW, ldg]; (dy_k + 1) | (dx_k + 1) << 2 is nibble k of a_slots / g_slots.  Several taps of a narrow convolution
+  // thus share one job (stacked along M or N); pixels outside their tensor and unused slots contribute zeros.
+  int AH, AW, lda, a_coff, a_sy, a_sx, a_sw, a_nslots;
+  int GH, GW, ldg, g_coff, g_sy, g_sx, g_sw, g_nslots, g_cout;
+  unsigned long long a_slots, g_slots;
 };
 int launch_wgrad_tc(const WgradTcArgs& a, cudaStream_t s);
 // up to three independent jobs (same C) in ONE launch, CTAs split between them: one accumulator flush per CTA instead of three
 int launch_wgrad_tc_multi(const WgradTcArgs* a, int n, cudaStream_t s);
 // weight gradient of a tap-class convolution (ConvGeom: the samplers' strided / transposed 3x3) on the tensor-core kernel:
-// one gathered one-tap C = 64 job per (tap, 64-channel block of CIN), all in ONE launch.  Same contract as
+// gathered C = 64 jobs (one per tap and 64-channel block of CIN; the taps of a narrow operand stacked), all in ONE launch.  Same contract as
 // launch_wgrad_taps, except that dW / db are overwritten (no zeroing by the caller); scratch: wgrad_gather_scratch_floats()
 bool wgrad_gather_ok(const ConvGeom& g);
 size_t wgrad_gather_scratch_floats();

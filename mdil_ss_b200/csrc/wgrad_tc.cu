@@ -290,6 +290,18 @@ wgrad_tc_kernel(const __grid_constant__ JobsT<NJ> jobs) {
         if (mine) return;
       }
     };
+    // gathered jobs: this thread's four channels belong to one slot of each operand (tap offsets, source channels)
+    int gen_ady = 0, gen_adx = 0, gen_gdy = 0, gen_gdx = 0, gen_ach = 0, gen_gch = 0;
+    bool gen_aon = false, gen_gon = false;
+    if (GEN) {
+      const int sa = ch / a.a_sw, sg = ch / a.g_sw;
+      const uint32_t na = (uint32_t)(a.a_slots >> (4 * sa)) & 15u, ng = (uint32_t)(a.g_slots >> (4 * sg)) & 15u;
+      gen_ady = (int)(na & 3u) - 1; gen_adx = (int)(na >> 2) - 1;
+      gen_gdy = (int)(ng & 3u) - 1; gen_gdx = (int)(ng >> 2) - 1;
+      gen_ach = a.a_coff + ch % a.a_sw; gen_gch = a.g_coff + ch % a.g_sw;
+      gen_aon = sa < a.a_nslots;
+      gen_gon = sg < a.g_nslots && ch % a.g_sw < a.g_cout;
+    }
     // register double buffer: the loads of batch n+1 are issued before batch n is split and stored
     const bool g_split = a.g_split != 0;
     auto load_batch = [&](FillDesc (&fd)[B], float4 (&av)[B][RPT], float4 (&gv)[B][RPT], uint32_t& inside) {
@@ -306,12 +318,12 @@ wgrad_tc_kernel(const __grid_constant__ JobsT<NJ> jobs) {
             const int v = fd[b].rv + d * (fd[b].vb * TP + row);
             if (GEN) {
               if (fd[b].uok && v < pl.V) {     // (u, v) = (row, column) of the virtual grid
-                const int ay = fd[b].u * a.a_sy + a.a_dy, ax = v * a.a_sx + a.a_dx;
-                if ((unsigned)ay < (unsigned)a.AH && (unsigned)ax < (unsigned)a.AW)
-                  av[b][i] = ldg4(a.A + ((size_t)(fd[b].n * a.AH + ay) * a.AW + ax) * a.lda + a.a_coff + ch);
-                const int gy = fd[b].u * a.g_sy + a.g_dy, gx = v * a.g_sx + a.g_dx;
-                if ((unsigned)gy < (unsigned)a.GH && (unsigned)gx < (unsigned)a.GW && ch < a.g_cout)
-                  gv[b][i] = ldg4(a.G + ((size_t)(fd[b].n * a.GH + gy) * a.GW + gx) * a.ldg + a.g_coff + ch);
+                const int ay = fd[b].u * a.a_sy + gen_ady, ax = v * a.a_sx + gen_adx;
+                if (gen_aon && (unsigned)ay < (unsigned)a.AH && (unsigned)ax < (unsigned)a.AW)
+                  av[b][i] = ldg4(a.A + ((size_t)(fd[b].n * a.AH + ay) * a.AW + ax) * a.lda + gen_ach);
+                const int gy = fd[b].u * a.g_sy + gen_gdy, gx = v * a.g_sx + gen_gdx;
+                if (gen_gon && (unsigned)gy < (unsigned)a.GH && (unsigned)gx < (unsigned)a.GW)
+                  gv[b][i] = ldg4(a.G + ((size_t)(fd[b].n * a.GH + gy) * a.GW + gx) * a.ldg + gen_gch);
               }
             } else if (fd[b].uok && v < pl.V) {
               const size_t off = fd[b].img + fd[b].u * su + v * sv + ch;
@@ -590,17 +602,32 @@ static int launch_gather(const WgradTcArgs* a, int n, cudaStream_t s) {
   return 0;
 }
 
-// accumulators of the gathered jobs -> dW in the caller's layout; bias sums -> db
-struct GatherUnpack { int n, cin, cout; int widx[kGatherJobs], ci0[kGatherJobs]; };
+// accumulators of the gathered jobs -> dW in the caller's layout; bias sums -> db.  Accumulator row m = slot_a * a_sw +
+// ci, column n = slot_g * g_sw + co; one of the operands is stacked (or neither): widx[job][stacked slot] = weight tap.
+struct GatherUnpack {
+  int n, cin, cout;
+  short ci0[kGatherJobs], a_sw[kGatherJobs], a_nslots[kGatherJobs], g_sw[kGatherJobs], g_nslots[kGatherJobs];
+  unsigned short bias_slots[kGatherJobs];     // gradient slots whose sums count for db (every class once)
+  signed char widx[kGatherJobs][16];
+};
 __global__ void wgrad_gather_unpack_kernel(const GatherUnpack gu, const float* __restrict__ acc, float* __restrict__ dW,
                                            long s_ci, long s_co, long s_t, const float* __restrict__ dbacc,
                                            float* __restrict__ db) {
   const int total = gu.n * 64 * 64;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
-    const int j = e >> 12, ci = gu.ci0[j] + ((e >> 6) & 63), co = e & 63;
-    if (ci < gu.cin && co < gu.cout) dW[(long)gu.widx[j] * s_t + (long)ci * s_ci + (long)co * s_co] = acc[e];
+    const int j = e >> 12, m = (e >> 6) & 63, n = e & 63;
+    const int sa = m / gu.a_sw[j], sg = n / gu.g_sw[j];
+    const int ci = gu.ci0[j] + m % gu.a_sw[j], co = n % gu.g_sw[j];
+    if (sa < gu.a_nslots[j] && sg < gu.g_nslots[j] && ci < gu.cin && co < gu.cout)
+      dW[(long)gu.widx[j][sa > sg ? sa : sg] * s_t + (long)ci * s_ci + (long)co * s_co] = acc[e];
   }
-  if (db != nullptr && blockIdx.x == 0 && threadIdx.x < gu.cout) db[threadIdx.x] = dbacc[threadIdx.x];
+  if (db != nullptr && blockIdx.x == 0 && threadIdx.x < gu.cout) {
+    float sum = 0.f;
+    for (int j = 0; j < gu.n; ++j)
+      for (int sg = 0; sg < gu.g_nslots[j]; ++sg)
+        if ((gu.bias_slots[j] >> sg) & 1) sum += dbacc[j * 64 + sg * gu.g_sw[j] + threadIdx.x];
+    db[threadIdx.x] = sum;
+  }
 }
 
 }  // namespace wtc
@@ -626,14 +653,25 @@ int launch_wgrad_tc_multi(const WgradTcArgs* a_in, int n, cudaStream_t s) {
 
 int launch_wgrad_tc(const WgradTcArgs& a, cudaStream_t s) { return launch_wgrad_tc_multi(&a, 1, s); }
 
+static inline unsigned long long gather_nibble(int dy, int dx, int slot) {
+  return (unsigned long long)((dy + 1) | ((dx + 1) << 2)) << (4 * slot);
+}
+
 bool wgrad_gather_ok(const ConvGeom& g) {
   static const bool on = [] { const char* e = getenv("MDIL_WGRAD_GATHER"); return !(e != nullptr && strcmp(e, "0") == 0); }();
   int taps = 0;
-  for (int c = 0; c < g.nclasses; ++c) taps += g.cls[c].ntaps;
-  return on && g.CIN % 64 == 0 && g.CIN_VALID == g.CIN && g.COUT % 4 == 0 && g.COUT <= 64 &&
-         taps * (g.CIN / 64) <= wtc::kGatherJobs && g.lda % 4 == 0 && g.a_coff % 4 == 0 && g.ldg % 4 == 0 && g.g_coff % 4 == 0;
+  for (int c = 0; c < g.nclasses; ++c) {
+    taps += g.cls[c].ntaps;
+    if (g.cls[c].o_dy < -1 || g.cls[c].o_dy > 1 || g.cls[c].o_dx < -1 || g.cls[c].o_dx > 1) return false;
+    for (int t = 0; t < g.cls[c].ntaps; ++t)
+      if (g.cls[c].a_dy[t] < -1 || g.cls[c].a_dy[t] > 1 || g.cls[c].a_dx[t] < -1 || g.cls[c].a_dx[t] > 1) return false;
+  }
+  if (!on || g.lda % 4 != 0 || g.a_coff % 4 != 0 || g.ldg % 4 != 0 || g.g_coff % 4 != 0 || g.COUT > 64) return false;
+  if (g.g_coff + (g.COUT + 3) / 4 * 4 > g.ldg) return false;
+  if (g.CIN % 64 == 0) return g.CIN_VALID == g.CIN && taps * (g.CIN / 64) <= wtc::kGatherJobs;
+  return (g.CIN == 4 || g.CIN == 16) && g.nclasses == 1;      // narrow input: taps stacked along M
 }
-size_t wgrad_gather_scratch_floats() { return (size_t)wtc::kGatherJobs * 64 * 64 + 64; }
+size_t wgrad_gather_scratch_floats() { return (size_t)wtc::kGatherJobs * (64 * 64 + 64); }
 
 int launch_wgrad_gather_tc(const ConvGeom& g, const float* A, const float* G, float* dW, long s_ci, long s_co, long s_t,
                            float* db, float* scratch, cudaStream_t s) {
@@ -645,24 +683,74 @@ int launch_wgrad_gather_tc(const ConvGeom& g, const float* A, const float* G, fl
   memset(&gu, 0, sizeof(gu));
   float* dbacc = scratch + (size_t)wtc::kGatherJobs * 64 * 64;
   int n = 0;
-  for (int c = 0; c < g.nclasses; ++c)
-    for (int t = 0; t < g.cls[c].ntaps; ++t)
-      for (int cb = 0; cb < g.CIN / 64; ++cb) {
-        WgradTcArgs& w = jobs[n];
-        memset(&w, 0, sizeof(w));
-        w.A = A; w.G = G; w.dWacc = scratch + (size_t)n * 64 * 64;
-        w.db = (db != nullptr && t == 0 && cb == 0) ? dbacc : nullptr;     // every class walks its gradient pixels once
-        w.N = g.N; w.H = g.VH; w.W = g.VW; w.C = 64; w.dil = 1; w.ntaps = 1; w.vert = 1; w.trace = trace;
-        w.AH = g.AH; w.AW = g.AW; w.lda = g.lda; w.a_coff = g.a_coff + 64 * cb; w.a_sy = g.a_sy; w.a_sx = g.a_sx;
-        w.a_dy = g.cls[c].a_dy[t]; w.a_dx = g.cls[c].a_dx[t];
-        w.GH = g.GH; w.GW = g.GW; w.ldg = g.ldg; w.g_coff = g.g_coff; w.g_sy = g.g_sy; w.g_sx = g.g_sx;
-        w.g_dy = g.cls[c].o_dy; w.g_dx = g.cls[c].o_dx; w.g_cout = g.COUT;
-        gu.widx[n] = g.cls[c].widx[t]; gu.ci0[n] = 64 * cb;
-        ++n;
+  auto new_job = [&](int ci0, int a_sw, int g_sw) -> WgradTcArgs& {
+    WgradTcArgs& w = jobs[n];
+    memset(&w, 0, sizeof(w));
+    w.A = A; w.G = G; w.dWacc = scratch + (size_t)n * 64 * 64; w.db = db != nullptr ? dbacc + n * 64 : nullptr;
+    w.N = g.N; w.H = g.VH; w.W = g.VW; w.C = 64; w.dil = 1; w.ntaps = 1; w.vert = 1; w.trace = trace;
+    w.AH = g.AH; w.AW = g.AW; w.lda = g.lda; w.a_coff = g.a_coff + ci0; w.a_sy = g.a_sy; w.a_sx = g.a_sx; w.a_sw = a_sw;
+    w.GH = g.GH; w.GW = g.GW; w.ldg = g.ldg; w.g_coff = g.g_coff; w.g_sy = g.g_sy; w.g_sx = g.g_sx; w.g_sw = g_sw;
+    w.g_cout = (g.COUT + 3) / 4 * 4;
+    gu.ci0[n] = (short)ci0; gu.a_sw[n] = (short)a_sw; gu.g_sw[n] = (short)g_sw;
+    return w;
+  };
+  if (g.CIN % 64 == 0 && g.COUT <= 16) {
+    // narrow output (64 -> 16 upsampler): the taps that read the same activation pixel share a job, their gradient
+    // pixels (one parity class each) stacked along N in 16-channel slots
+    bool class_counted[kMaxClasses] = {false, false, false, false};
+    for (int dy = -1; dy <= 1; ++dy)
+      for (int dx = -1; dx <= 1; ++dx)
+        for (int cb = 0; cb < g.CIN / 64; ++cb) {
+          int slots = 0;
+          for (int c = 0; c < g.nclasses; ++c)
+            for (int t = 0; t < g.cls[c].ntaps; ++t)
+              if (g.cls[c].a_dy[t] == dy && g.cls[c].a_dx[t] == dx) {
+                MDIL_REQUIRE(n < wtc::kGatherJobs, "wgrad_gather: job count");
+                WgradTcArgs& w = slots == 0 ? new_job(64 * cb, 64, 16) : jobs[n];
+                if (slots == 0) { w.a_slots = gather_nibble(dy, dx, 0); w.a_nslots = 1; }
+                MDIL_REQUIRE(slots < 4, "wgrad_gather: slot count");
+                w.g_slots |= gather_nibble(g.cls[c].o_dy, g.cls[c].o_dx, slots);
+                gu.widx[n][slots] = (signed char)g.cls[c].widx[t];
+                if (cb == 0 && !class_counted[c]) { gu.bias_slots[n] |= (unsigned short)(1u << slots); class_counted[c] = true; }
+                w.g_nslots = ++slots;
+              }
+          if (slots > 0) { gu.a_nslots[n] = 1; gu.g_nslots[n] = (short)slots; ++n; }
+        }
+  } else if (g.CIN % 64 == 0) {
+    // one job per (tap, 64-channel block of CIN)
+    for (int c = 0; c < g.nclasses; ++c)
+      for (int t = 0; t < g.cls[c].ntaps; ++t)
+        for (int cb = 0; cb < g.CIN / 64; ++cb) {
+          MDIL_REQUIRE(n < wtc::kGatherJobs, "wgrad_gather: job count");
+          WgradTcArgs& w = new_job(64 * cb, 64, 64);
+          w.a_slots = gather_nibble(g.cls[c].a_dy[t], g.cls[c].a_dx[t], 0); w.a_nslots = 1;
+          w.g_slots = gather_nibble(g.cls[c].o_dy, g.cls[c].o_dx, 0); w.g_nslots = 1;
+          gu.widx[n][0] = (signed char)g.cls[c].widx[t];
+          gu.a_nslots[n] = 1; gu.g_nslots[n] = 1;
+          if (t == 0 && cb == 0) gu.bias_slots[n] = 1;     // every class walks its gradient pixels once
+          ++n;
+        }
+  } else {
+    // narrow input (3 -> 16, 16 -> 64 downsamplers; one tap class): taps stacked along M in CIN-channel slots
+    const TapClass& tc = g.cls[0];
+    const int per_max = 64 / g.CIN, nj = cdiv(tc.ntaps, per_max), per = cdiv(tc.ntaps, nj);
+    for (int t0 = 0; t0 < tc.ntaps; t0 += per) {
+      MDIL_REQUIRE(n < wtc::kGatherJobs, "wgrad_gather: job count");
+      WgradTcArgs& w = new_job(0, g.CIN, 64);
+      const int cnt = tc.ntaps - t0 < per ? tc.ntaps - t0 : per;
+      for (int k = 0; k < cnt; ++k) {
+        w.a_slots |= gather_nibble(tc.a_dy[t0 + k], tc.a_dx[t0 + k], k);
+        gu.widx[n][k] = (signed char)tc.widx[t0 + k];
       }
+      w.a_nslots = cnt;
+      w.g_slots = gather_nibble(tc.o_dy, tc.o_dx, 0); w.g_nslots = 1;
+      gu.a_nslots[n] = (short)cnt; gu.g_nslots[n] = 1;
+      if (t0 == 0) gu.bias_slots[n] = 1;
+      ++n;
+    }
+  }
   gu.n = n; gu.cin = g.CIN_VALID; gu.cout = g.COUT;
-  MDIL_CUDA(cudaMemsetAsync(scratch, 0, sizeof(float) * ((size_t)n * 64 * 64), s));
-  MDIL_CUDA(cudaMemsetAsync(dbacc, 0, sizeof(float) * 64, s));
+  MDIL_CUDA(cudaMemsetAsync(scratch, 0, sizeof(float) * wgrad_gather_scratch_floats(), s));
   MDIL_TRY(wtc::launch_gather(jobs, n, s));
   int grid = (n * 64 * 64 + 255) / 256;
   if (grid > kNumSMs) grid = kNumSMs;

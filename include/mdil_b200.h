@@ -162,6 +162,13 @@ int mdil_outconv_bwd(const float* dlogits, const float* x, const float* w, float
  * mdil_ce2d_scale time). */
 int mdil_ce2d_fwd_bwd(const float* logits, const int64_t* labels, const float* class_w, int N, int C, int H, int W,
                       float* loss, double* acc /*[2]*/, float* dlogits /*may be NULL*/, void* stream);
+/* Two-phase form (what the autograd function of the host layer uses): mdil_ce2d_fwd_bwd with dlogits = NULL reads the
+ * logits once and writes only loss / acc; mdil_ce2d_bwd then recomputes the softmax from the same logits and writes
+ * dlogits = w[y] * (softmax - onehot) * (*grad_out) / acc[1] (grad_out: device scalar, may be NULL = 1; acc may have been
+ * all-reduced over the ranks in between: SURVEY 8e).  Replaces the backward of CrossEntropyLoss2d,
+ * train_new_task_step2.py:84-92. */
+int mdil_ce2d_bwd(const float* logits, const int64_t* labels, const float* class_w, int N, int C, int H, int W,
+                  const double* acc /*[2]*/, const float* grad_out, float* dlogits, void* stream);
 /* dlogits *= (*grad_out) / acc[1]  (grad_out: device scalar, may be NULL = 1). */
 int mdil_ce2d_scale(float* dlogits, size_t n, const double* acc, const float* grad_out, void* stream);
 

@@ -21,7 +21,7 @@ EXPORTS = [
     "mdil_down_packed_floats", "mdil_down_workspace_bytes", "mdil_down_pack", "mdil_down_fwd", "mdil_down_bwd",
     "mdil_up_packed_floats", "mdil_up_workspace_bytes", "mdil_up_pack", "mdil_up_fwd", "mdil_up_bwd",
     "mdil_outconv_fwd", "mdil_outconv_bwd",
-    "mdil_ce2d_fwd_bwd", "mdil_ce2d_scale", "mdil_kd_fwd_bwd", "mdil_scale_by_device_scalar",
+    "mdil_ce2d_fwd_bwd", "mdil_ce2d_bwd", "mdil_ce2d_scale", "mdil_kd_fwd_bwd", "mdil_scale_by_device_scalar",
     "mdil_argmax_confusion", "mdil_adam_step", "mdil_launch_count", "mdil_profile_begin", "mdil_profile_end",
     "mdil_cotransform", "mdil_adam_step_dev",
 ]
@@ -97,6 +97,7 @@ def _declare(lib) -> None:
     lib.mdil_outconv_fwd.argtypes = [vp, vp, vp, vp, i, i, i, i, vp]
     lib.mdil_outconv_bwd.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, vp]
     lib.mdil_ce2d_fwd_bwd.argtypes = [vp, vp, vp, i, i, i, i, vp, vp, vp, vp]
+    lib.mdil_ce2d_bwd.argtypes = [vp, vp, vp, i, i, i, i, vp, vp, vp, vp]
     lib.mdil_ce2d_scale.argtypes = [vp, sz, vp, vp, vp]
     lib.mdil_kd_fwd_bwd.argtypes = [vp, vp, i, i, i, i, vp, vp, vp, vp]
     lib.mdil_scale_by_device_scalar.argtypes = [vp, sz, vp, vp]

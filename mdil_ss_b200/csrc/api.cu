@@ -735,6 +735,13 @@ int mdil_ce2d_fwd_bwd(const float* logits, const int64_t* labels, const float* c
   return launch_ce2d(logits, labels, class_w, N, C, H, W, loss, acc, dlogits, S(stream));
 }
 
+int mdil_ce2d_bwd(const float* logits, const int64_t* labels, const float* class_w, int N, int C, int H, int W,
+                  const double* acc, const float* grad_out, float* dlogits, void* stream) {
+  MDIL_REQUIRE(logits != nullptr && labels != nullptr && class_w != nullptr && acc != nullptr && dlogits != nullptr,
+               "ce2d_bwd: null argument");
+  return launch_ce2d_bwd(logits, labels, class_w, N, C, H, W, acc, grad_out, dlogits, S(stream));
+}
+
 int mdil_ce2d_scale(float* dlogits, size_t n, const double* acc, const float* grad_out, void* stream) {
   return launch_scale(dlogits, n, acc + 1, grad_out, S(stream));
 }

@@ -182,6 +182,9 @@ int launch_outconv_bwd(const float* dlogits, const float* x, const float* w, flo
                        int H, int W, int Ccls, cudaStream_t s);
 int launch_ce2d(const float* logits, const int64_t* labels, const float* class_w, int N, int C, int H, int W,
                 float* loss, double* acc, float* dlogits, cudaStream_t s);
+// logit gradient of launch_ce2d recomputed from the logits: w[y] * (softmax - onehot) * (*grad_out or 1) / acc[1]
+int launch_ce2d_bwd(const float* logits, const int64_t* labels, const float* class_w, int N, int C, int H, int W,
+                    const double* acc, const float* grad_out, float* dlogits, cudaStream_t s);
 int launch_kd(const float* student, const float* teacher, int N, int C, int H, int W, float* loss, double* acc,
               float* dstudent, cudaStream_t s);
 int launch_argmax_confusion(const float* logits, const int64_t* labels, int N, int C, int H, int W, int64_t* pred,

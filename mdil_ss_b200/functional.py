@@ -406,7 +406,8 @@ class OutConvFn(torch.autograd.Function):
 # ======================================================================================= losses
 class CrossEntropy2dFn(torch.autograd.Function):
     """CrossEntropyLoss2d.forward (train_new_task_step2.py:84-92): NLLLoss(weight)(log_softmax(logits, 1), target).
-    One fused pass produces the loss and the (unnormalised) logit gradient."""
+    Two passes over the logits: the forward reads them once for the loss sums; the backward recomputes the softmax and
+    writes the logit gradient already scaled by grad_out / sum(w) (mdil_ce2d_bwd)."""
 
     @staticmethod
     def forward(ctx, logits, target, weight, group_norm=None):
@@ -425,10 +426,8 @@ class CrossEntropy2dFn(torch.autograd.Function):
             weight = weight.to(device=logits.device, dtype=torch.float32).contiguous()
             loss = torch.empty((), device=logits.device, dtype=torch.float32)
             acc = torch.empty(2, device=logits.device, dtype=torch.float64)
-            need = ctx.needs_input_grad[0]
-            dlogits = torch.empty_like(logits) if need else None
             L.check(lib.mdil_ce2d_fwd_bwd(logits.data_ptr(), target.data_ptr(), weight.data_ptr(), n, c, h, w,
-                                          loss.data_ptr(), acc.data_ptr(), _ptr(dlogits), _stream()), "mdil_ce2d_fwd_bwd")
+                                          loss.data_ptr(), acc.data_ptr(), None, _stream()), "mdil_ce2d_fwd_bwd")
             ctx.world = 1
             if group_norm is not None:
                 # nn.DataParallel computes the loss on the gathered logits: sum(w*nll) / sum(w) over the GLOBAL batch
@@ -440,23 +439,21 @@ class CrossEntropy2dFn(torch.autograd.Function):
                     dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=grp)
                     ctx.world = dist.get_world_size(grp)
                     loss = (acc[0] / acc[1]).to(torch.float32)
-        ctx.internal = (dlogits, acc)
+        ctx.save_for_backward(logits, target, weight, acc)
         return loss
 
     @staticmethod
     def backward(ctx, grad_out):
-        lib = L.lib()
-        dlogits, acc = ctx.internal
-        if dlogits is None:
-            if ctx.needs_input_grad[0]:
-                raise RuntimeError("cross_entropy2d: the fused logit gradient is single-use (scaled in place); a second "
-                                   "backward through the same loss (retain_graph=True) is not supported")
+        if not ctx.needs_input_grad[0]:
             return None, None, None, None
-        ctx.internal = (None, None)  # single use: the stash is scaled in place
-        with torch.cuda.device_of(dlogits):
+        lib = L.lib()
+        logits, target, weight, acc = ctx.saved_tensors
+        n, c, h, w = logits.shape
+        with torch.cuda.device_of(logits):
             g = (grad_out.to(dtype=torch.float32) * float(ctx.world)).contiguous()
-            L.check(lib.mdil_ce2d_scale(dlogits.data_ptr(), dlogits.numel(), acc.data_ptr(), g.data_ptr(), _stream()),
-                    "mdil_ce2d_scale")
+            dlogits = torch.empty_like(logits)
+            L.check(lib.mdil_ce2d_bwd(logits.data_ptr(), target.data_ptr(), weight.data_ptr(), n, c, h, w, acc.data_ptr(),
+                                      g.data_ptr(), dlogits.data_ptr(), _stream()), "mdil_ce2d_bwd")
         return dlogits, None, None, None
 
 

@@ -260,9 +260,9 @@ static int nb1d_fwd_p4(const mdil_nb1d_desc* d, const float* x, const mdil_nb1d_
   a.b1 = p4_bias(packed, 2); a.b2 = p4_bias(packed, 3);
   a.mid_out = d->save ? sv->c : nullptr; a.out = sv->s; a.sums = d->train ? sums2 : nullptr;
   MDIL_TRY(launch_pair(a, s));
-  MDIL_TRY(launch_bn_finalize(sums2, CP, count, C, w->bn2.weight, w->bn2.bias, w->bn2.running_mean, w->bn2.running_var,
-                              d->eps, d->momentum, d->train, st2, s, 4, nullptr));
-  return launch_bn_act(sv->s, st2, drop_mask, x, y, d->N, HW, C, s);
+  // y = relu(bn2(s) * drop + x), the BatchNorm finalisation in the same launch
+  return launch_bn_act_fused(sv->s, sums2, CP, count, w->bn2.weight, w->bn2.bias, w->bn2.running_mean, w->bn2.running_var,
+                             d->eps, d->momentum, d->train, 4, st2, drop_mask, x, y, d->N, HW, C, s);
 }
 
 int mdil_nb1d_fwd(const mdil_nb1d_desc* d, const float* x, const mdil_nb1d_weights* w, const float* packed,
@@ -310,11 +310,9 @@ int mdil_nb1d_fwd(const mdil_nb1d_desc* d, const float* x, const mdil_nb1d_weigh
   a.b1 = w->b31_2; a.b2 = w->b13_2; a.bad = d->has_adapter ? w->bp2 : nullptr;
   a.mid_out = d->save ? sv->c : nullptr; a.out = sv->s; a.sums = d->train ? sums2 : nullptr; a.dil = d->dil;
   MDIL_TRY(launch_pair(a, s));
-  MDIL_TRY(launch_bn_finalize(sums2, C, count, C, w->bn2.weight, w->bn2.bias, w->bn2.running_mean, w->bn2.running_var,
-                              d->eps, d->momentum, d->train, st2, s));
-  // y = relu(bn2(s) * drop + x)
-  MDIL_TRY(launch_bn_act(sv->s, st2, drop_mask, x, y, d->N, HW, C, s));
-  return 0;
+  // y = relu(bn2(s) * drop + x), the BatchNorm finalisation in the same launch
+  return launch_bn_act_fused(sv->s, sums2, C, count, w->bn2.weight, w->bn2.bias, w->bn2.running_mean, w->bn2.running_var,
+                             d->eps, d->momentum, d->train, 1, st2, drop_mask, x, y, d->N, HW, C, s);
 }
 
 // One weight gradient of the block: tensor-core path (C = 64, 128) or the generic FFMA tap kernel.
@@ -381,8 +379,7 @@ static int nb1d_bwd_p4(const mdil_nb1d_desc* d, const float* dy, const float* x,
   Carver cv(ws);
   double* sums2 = cv.take<double>(2 * C + 2 * CP);   // BN2 backward sums [2][16], then BN1's per (slot, channel) [2][64]
   double* sums1 = sums2 + 2 * C;
-  float* coef2 = cv.take<float>(3 * C);
-  float* coef1 = cv.take<float>(3 * C);
+  (void)cv.take<float>(6 * C);     // (coefficient buffers of the unfused BatchNorm backward: layout kept)
   float* rep1 = cv.take<float>(4 * CP);
   float* T1 = cv.take<float>(T);
   float* T2 = cv.take<float>(T);
@@ -400,9 +397,9 @@ static int nb1d_bwd_p4(const mdil_nb1d_desc* d, const float* dy, const float* x,
 
   // ---- BN2 backward (+ ReLU mask of y, dropout): ds  (elementwise kernels on the 16-channel view)
   MDIL_TRY(launch_bn_bwd_stats(dy, y, drop_mask, sv->s, st2, sums2, N, HW, C, s));
-  MDIL_TRY(launch_bn_bwd_finalize(sums2, count, C, w->bn2.weight, st2, coef2, gr->bn2_w, gr->bn2_b, s));
   const int s16 = s16_enabled() ? 1 : 0;
-  MDIL_TRY(launch_bn_bwd_apply(dy, y, drop_mask, sv->s, st2, coef2, T1, N, HW, C, s, s16));
+  MDIL_TRY(launch_bn_bwd_apply_fused(dy, y, drop_mask, sv->s, st2, sums2, count, w->bn2.weight, 1, gr->bn2_w, gr->bn2_b, T1, N,
+                                     HW, C, s, s16));
 
   // ---- pair 2 backward: ds -> dc' -> dq (masked by r>0), sums for BN1 backward
   PairArgs a;
@@ -419,8 +416,8 @@ static int nb1d_bwd_p4(const mdil_nb1d_desc* d, const float* dy, const float* x,
   MDIL_TRY(flush_wgrad_jobs(&jl, s));
 
   // ---- BN1 backward: dq -> dp (overwrites ds)
-  MDIL_TRY(launch_bn_bwd_finalize(sums1, count, C, w->bn1.weight, st1, coef1, gr->bn1_w, gr->bn1_b, s, 4));
-  MDIL_TRY(launch_bn_bwd_apply(T3, nullptr, nullptr, sv->p, st1, coef1, T1, N, HW, C, s, s16));
+  MDIL_TRY(launch_bn_bwd_apply_fused(T3, nullptr, nullptr, sv->p, st1, sums1, count, w->bn1.weight, 4, gr->bn1_w, gr->bn1_b, T1,
+                                     N, HW, C, s, s16));
 
   // ---- pair 1 backward: dp -> da' -> dx (+ residual dy * (y>0))
   a.in = T1; a.wstream_tc = p4_stream(packed, 3); a.mid_mask = sv->a; a.mid_out = T2; a.out = dx;
@@ -450,8 +447,7 @@ int mdil_nb1d_bwd(const mdil_nb1d_desc* d, const float* dy, const float* x, cons
   Carver cv(ws);
   double* sums2 = cv.take<double>(4 * C);     // [2][2][C]: both BatchNorms' backward sums, one memset
   double* sums1 = sums2 + 2 * C;
-  float* coef2 = cv.take<float>(3 * C);
-  float* coef1 = cv.take<float>(3 * C);
+  (void)cv.take<float>(6 * C);     // (coefficient buffers of the unfused BatchNorm backward: layout kept)
   float* T1 = cv.take<float>(T);
   float* T2 = cv.take<float>(T);
   float* T3 = cv.take<float>(T);
@@ -467,9 +463,9 @@ int mdil_nb1d_bwd(const mdil_nb1d_desc* d, const float* dy, const float* x, cons
 
   // ---- BN2 backward (+ ReLU mask of y, dropout): ds
   MDIL_TRY(launch_bn_bwd_stats(dy, y, drop_mask, sv->s, st2, sums2, N, HW, C, s));
-  MDIL_TRY(launch_bn_bwd_finalize(sums2, count, C, w->bn2.weight, st2, coef2, gr->bn2_w, gr->bn2_b, s));
   const int s16 = (s16_enabled() && use_tensor_cores(C) && use_tc_wgrad(C)) ? 1 : 0;
-  MDIL_TRY(launch_bn_bwd_apply(dy, y, drop_mask, sv->s, st2, coef2, T1, N, HW, C, s, s16));
+  MDIL_TRY(launch_bn_bwd_apply_fused(dy, y, drop_mask, sv->s, st2, sums2, count, w->bn2.weight, 1, gr->bn2_w, gr->bn2_b, T1, N,
+                                     HW, C, s, s16));
   static const int stop = [] { const char* dbg = getenv("MDIL_DEBUG_STOP"); return dbg ? atoi(dbg) : 0; }();   // tools/debug_nb1d.py
   if (stop == 1) return 0;
 
@@ -494,8 +490,8 @@ int mdil_nb1d_bwd(const mdil_nb1d_desc* d, const float* dy, const float* x, cons
 
   if (stop == 3) return 0;
   // ---- BN1 backward: dq -> dp (overwrites ds)
-  MDIL_TRY(launch_bn_bwd_finalize(sums1, count, C, w->bn1.weight, st1, coef1, gr->bn1_w, gr->bn1_b, s));
-  MDIL_TRY(launch_bn_bwd_apply(T3, nullptr, nullptr, sv->p, st1, coef1, T1, N, HW, C, s, s16));
+  MDIL_TRY(launch_bn_bwd_apply_fused(T3, nullptr, nullptr, sv->p, st1, sums1, count, w->bn1.weight, 1, gr->bn1_w, gr->bn1_b, T1,
+                                     N, HW, C, s, s16));
 
   // ---- pair 1 backward: dp -> da' -> dx (+ residual dy * (y>0))
   a.in = T1; a.wstream = packed + 21 * CC; a.wstream_tc = tc_stream(packed, C, 3); a.mid_mask = sv->a; a.mid_out = T2; a.out = dx;
@@ -550,10 +546,8 @@ static int bn_forward_tail(const float* u, size_t P, int C, const mdil_bn_params
     MDIL_CUDA(cudaMemsetAsync(sums, 0, 2 * C * sizeof(double), s));
     MDIL_TRY(launch_channel_stats(u, P, C, 0, C, sums, C, s));
   }
-  MDIL_TRY(launch_bn_finalize(sums, C, (double)P, C, bn->weight, bn->bias, bn->running_mean, bn->running_var, eps,
-                              momentum, train, stats, s));
-  MDIL_TRY(launch_bn_act(u, stats, nullptr, nullptr, y, N, HW, C, s));
-  return 0;
+  return launch_bn_act_fused(u, sums, C, (double)P, bn->weight, bn->bias, bn->running_mean, bn->running_var, eps, momentum,
+                             train, 1, stats, nullptr, nullptr, y, N, HW, C, s);
 }
 
 int mdil_down_fwd(const mdil_down_desc* d, const float* x, const float* packed, const float* bias,
@@ -588,12 +582,12 @@ int mdil_down_bwd(const mdil_down_desc* d, const float* dy, const float* x, cons
   const size_t OHW = (size_t)OH * OW;
   Carver cv(ws);
   double* sums = cv.take<double>(2 * Cout);
-  float* coef = cv.take<float>(3 * Cout);
+  (void)cv.take<float>(3 * Cout);
   float* du = cv.take<float>((size_t)d->N * OHW * Cout);
   MDIL_CUDA(cudaMemsetAsync(sums, 0, 2 * Cout * sizeof(double), s));
   MDIL_TRY(launch_bn_bwd_stats(dy, y, nullptr, u, stats, sums, d->N, OHW, Cout, s));
-  MDIL_TRY(launch_bn_bwd_finalize(sums, (double)d->N * OHW, Cout, bn->weight, stats, coef, dgamma, dbeta, s));
-  MDIL_TRY(launch_bn_bwd_apply(dy, y, nullptr, u, stats, coef, du, d->N, OHW, Cout, s));
+  MDIL_TRY(launch_bn_bwd_apply_fused(dy, y, nullptr, u, stats, sums, (double)d->N * OHW, bn->weight, 1, dgamma, dbeta, du, d->N,
+                                     OHW, Cout, s));
   if (dw != nullptr) {
     ConvGeom g;
     memset(&g, 0, sizeof(g));
@@ -688,12 +682,12 @@ int mdil_up_bwd(const mdil_up_desc* d, const float* dy, const float* x, const fl
   const size_t OHW = (size_t)4 * d->H * d->W;
   Carver cv(ws);
   double* sums = cv.take<double>(2 * Cout);
-  float* coef = cv.take<float>(3 * Cout);
+  (void)cv.take<float>(3 * Cout);
   float* du = cv.take<float>((size_t)d->N * OHW * Cout);
   MDIL_CUDA(cudaMemsetAsync(sums, 0, 2 * Cout * sizeof(double), s));
   MDIL_TRY(launch_bn_bwd_stats(dy, y, nullptr, u, stats, sums, d->N, OHW, Cout, s));
-  MDIL_TRY(launch_bn_bwd_finalize(sums, (double)d->N * OHW, Cout, bn->weight, stats, coef, dgamma, dbeta, s));
-  MDIL_TRY(launch_bn_bwd_apply(dy, y, nullptr, u, stats, coef, du, d->N, OHW, Cout, s));
+  MDIL_TRY(launch_bn_bwd_apply_fused(dy, y, nullptr, u, stats, sums, (double)d->N * OHW, bn->weight, 1, dgamma, dbeta, du, d->N,
+                                     OHW, Cout, s));
   if (dw != nullptr) {
     ConvGeom g = up_parity_geom(d);
     if (wgrad_gather_ok(g)) {     // 128 -> 64, 64 -> 16: gathered one-tap jobs on the tensor-core kernel

@@ -203,6 +203,78 @@ bn_act_kernel(const float* __restrict__ u, const float* __restrict__ stats, cons
   }
 }
 
+// bn_finalize + bn_act in one launch (C <= 128): every CTA derives scale / shift from the fp64 sums (train) or the
+// running statistics (eval) in its prologue; CTA 0 also writes the statistics block and updates the running statistics
+// (it reads rm / rv before it writes them; the other CTAs of a train-mode launch do not read them at all).
+__global__ void __launch_bounds__(256)
+bn_act_fused_kernel(const float* __restrict__ u, const double* __restrict__ sums, int ldsum, double count,
+                    const float* __restrict__ gamma, const float* __restrict__ beta, float* rm, float* rv, float eps,
+                    float momentum, int train, int fold, float* __restrict__ stats, const float* __restrict__ drop,
+                    const float* __restrict__ res, float* __restrict__ y, size_t total4, size_t HWC4, int C) {
+  __shared__ __align__(16) float cf[2 * 128];      // scale, shift
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float mean, var;
+    double unbiased = 0.0;
+    if (train) {
+      double s1 = 0.0, s2 = 0.0;
+      for (int p = 0; p < fold; ++p) { s1 += sums[p * C + c]; s2 += sums[ldsum + p * C + c]; }
+      const double m = s1 / count;
+      double v = s2 / count - m * m;
+      if (v < 0.0) v = 0.0;
+      mean = (float)m;
+      var = (float)v;
+      unbiased = count > 1.0 ? v * count / (count - 1.0) : v;
+    } else {
+      mean = rm[c];
+      var = rv[c];
+    }
+    const float invstd = 1.0f / sqrtf(var + eps);
+    const float scale = gamma[c] * invstd;
+    const float shift = beta[c] - mean * scale;
+    cf[c] = scale;
+    cf[C + c] = shift;
+    if (blockIdx.x == 0) {
+      if (train) {
+        rm[c] = (1.f - momentum) * rm[c] + momentum * mean;
+        rv[c] = (1.f - momentum) * rv[c] + momentum * (float)unbiased;
+      }
+      stats[c] = mean;
+      stats[C + c] = invstd;
+      stats[2 * C + c] = scale;
+      stats[3 * C + c] = shift;
+    }
+  }
+  __syncthreads();
+  const int C4 = C >> 2;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % C4);
+    float4 v = ldg4(u + i * 4);
+    const float4 sc = *reinterpret_cast<const float4*>(cf + c4 * 4), sh = *reinterpret_cast<const float4*>(cf + C + c4 * 4);
+    v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+    if (drop != nullptr) {
+      const float4 d = ldg4(drop + (i / HWC4) * C + c4 * 4);
+      v.x *= d.x; v.y *= d.y; v.z *= d.z; v.w *= d.w;
+    }
+    if (res != nullptr) {
+      const float4 r = ldg4(res + i * 4);
+      v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+    }
+    v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+    reinterpret_cast<float4*>(y)[i] = v;
+  }
+}
+
+int launch_bn_act_fused(const float* u, const double* sums, int ldsum, double count, const float* gamma, const float* beta,
+                        float* rm, float* rv, float eps, float momentum, int train, int fold, float* stats, const float* drop,
+                        const float* res, float* y, int N, size_t HW, int C, cudaStream_t s) {
+  MDIL_REQUIRE(C % 4 == 0 && C <= 128, "bn_act_fused: C % 4, C <= 128");
+  size_t total4 = (size_t)N * HW * (C / 4);
+  bn_act_fused_kernel<<<ew_grid(total4, 256), 256, 0, s>>>(u, sums, ldsum, count, gamma, beta, rm, rv, eps, momentum, train, fold,
+                                                           stats, drop, res, y, total4, HW * (C / 4), C);
+  MDIL_LAUNCH_CHECK();
+  return 0;
+}
+
 int launch_bn_act(const float* u, const float* stats, const float* drop, const float* res, float* y, int N, size_t HW,
                   int C, cudaStream_t s) {
   MDIL_REQUIRE(C % 4 == 0, "bn_act: C % 4");
@@ -277,6 +349,73 @@ bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ y, c
       reinterpret_cast<float4*>(du)[i] = o;
     }
   }
+}
+
+// bn_bwd_finalize + bn_bwd_apply in one launch: every CTA derives the per-channel coefficients from the fp64 sums in its
+// prologue (<= 128 channels: a handful of fp64 operations per CTA) and keeps them, with mean / invstd, in shared memory;
+// CTA 0 also writes the affine gradients.  One dependent launch less per BatchNorm backward (39 per training step).
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_fused_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ drop,
+                          const float* __restrict__ u, const float* __restrict__ stats, const double* __restrict__ sums,
+                          double count, const float* __restrict__ gamma, int fold, float* __restrict__ dgamma,
+                          float* __restrict__ dbeta, float* __restrict__ du, size_t total4, size_t HWC4, int C, int split) {
+  __shared__ __align__(16) float cf[5 * 128];      // g, k1, k2, mean, invstd
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    double sdz = 0.0, sdzu = 0.0;      // fold > 1: sums are [2][fold * C] per (pixel slot, channel)
+    for (int p = 0; p < fold; ++p) { sdz += sums[p * C + c]; sdzu += sums[fold * C + p * C + c]; }
+    cf[c] = __ldg(gamma + c) * __ldg(stats + C + c);
+    cf[C + c] = (float)(sdz / count);
+    cf[2 * C + c] = (float)(sdzu / count);
+    cf[3 * C + c] = __ldg(stats + c);
+    cf[4 * C + c] = __ldg(stats + C + c);
+    if (blockIdx.x == 0) {
+      if (dgamma != nullptr) dgamma[c] = (float)sdzu;
+      if (dbeta != nullptr) dbeta[c] = (float)sdz;
+    }
+  }
+  __syncthreads();
+  const int C4 = C >> 2;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % C4);
+    float4 v = ldg4(dy + i * 4);
+    if (y != nullptr) {
+      const float4 yy = ldg4(y + i * 4);
+      v.x = yy.x > 0.f ? v.x : 0.f; v.y = yy.y > 0.f ? v.y : 0.f;
+      v.z = yy.z > 0.f ? v.z : 0.f; v.w = yy.w > 0.f ? v.w : 0.f;
+    }
+    if (drop != nullptr) {
+      const float4 d = ldg4(drop + (i / HWC4) * C + c4 * 4);
+      v.x *= d.x; v.y *= d.y; v.z *= d.z; v.w *= d.w;
+    }
+    const float4 uu = ldg4(u + i * 4);
+    const float4 g = *reinterpret_cast<const float4*>(cf + c4 * 4), k1 = *reinterpret_cast<const float4*>(cf + C + c4 * 4),
+                 k2 = *reinterpret_cast<const float4*>(cf + 2 * C + c4 * 4), mean = *reinterpret_cast<const float4*>(cf + 3 * C + c4 * 4),
+                 istd = *reinterpret_cast<const float4*>(cf + 4 * C + c4 * 4);
+    float4 o;
+    o.x = g.x * (v.x - k1.x - (uu.x - mean.x) * istd.x * k2.x);
+    o.y = g.y * (v.y - k1.y - (uu.y - mean.y) * istd.y * k2.y);
+    o.z = g.z * (v.z - k1.z - (uu.z - mean.z) * istd.z * k2.z);
+    o.w = g.w * (v.w - k1.w - (uu.w - mean.w) * istd.w * k2.w);
+    if (split) {       // S16 format: see bn_bwd_apply_kernel
+      uint4 w;
+      split_bf16x2(o.x, o.y, w.x, w.z);
+      split_bf16x2(o.z, o.w, w.y, w.w);
+      reinterpret_cast<uint4*>(du)[i] = w;
+    } else {
+      reinterpret_cast<float4*>(du)[i] = o;
+    }
+  }
+}
+
+int launch_bn_bwd_apply_fused(const float* dy, const float* y, const float* drop, const float* u, const float* stats,
+                              const double* sums, double count, const float* gamma, int fold, float* dgamma, float* dbeta,
+                              float* du, int N, size_t HW, int C, cudaStream_t s, int split) {
+  MDIL_REQUIRE(C % 4 == 0 && C <= 128, "bn_bwd_apply_fused: C % 4, C <= 128");
+  size_t total4 = (size_t)N * HW * (C / 4);
+  bn_bwd_apply_fused_kernel<<<ew_grid(total4, 256), 256, 0, s>>>(dy, y, drop, u, stats, sums, count, gamma, fold, dgamma, dbeta,
+                                                                 du, total4, HW * (C / 4), C, split);
+  MDIL_LAUNCH_CHECK();
+  return 0;
 }
 
 int launch_bn_bwd_apply(const float* dy, const float* y, const float* drop, const float* u, const float* stats,

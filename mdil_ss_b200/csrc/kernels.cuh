@@ -32,6 +32,14 @@ int launch_bn_bwd_finalize(const double* sums, double count, int C, const float*
                            float* dgamma, float* dbeta, cudaStream_t s, int fold = 1);   // fold: sums are [2][fold*C]
 
 // du = coef0 * (dz - coef1 - uhat*coef2)
+// launch_bn_finalize + launch_bn_act in one launch (C <= 128; no replicated statistics)
+int launch_bn_act_fused(const float* u, const double* sums, int ldsum, double count, const float* gamma, const float* beta,
+                        float* rm, float* rv, float eps, float momentum, int train, int fold, float* stats, const float* drop,
+                        const float* res, float* y, int N, size_t HW, int C, cudaStream_t s);
+// launch_bn_bwd_finalize + launch_bn_bwd_apply in one launch (C <= 128)
+int launch_bn_bwd_apply_fused(const float* dy, const float* y, const float* drop, const float* u, const float* stats,
+                              const double* sums, double count, const float* gamma, int fold, float* dgamma, float* dbeta,
+                              float* du, int N, size_t HW, int C, cudaStream_t s, int split = 0);
 // split != 0: du is written in the "S16" format (per group of 4 channels = 16 bytes: 4 bf16 hi halves, 4 bf16 lo halves; x = hi + lo)
 int launch_bn_bwd_apply(const float* dy, const float* y, const float* drop, const float* u, const float* stats,
                         const float* coef, float* du, int N, size_t HW, int C, cudaStream_t s, int split = 0);

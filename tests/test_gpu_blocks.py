@@ -208,7 +208,10 @@ def test_upsampler(cin, cout, N, H, W, train):
             assert_close(gd[n[len("blk."):]], ref, TOL, n, atol=1e-4)
 
 
-@pytest.mark.parametrize("ccls,N,H,W", [(20, 2, 8, 12), (27, 1, 16, 32), (20, 1, 33, 65)])
+# even W: vectorised forward + one-pass fused backward (64-pixel tiles: W = 70 and 130 end in partial tiles; 27 and 32
+# classes use the wider mma column tilings); odd W: the scalar kernels
+@pytest.mark.parametrize("ccls,N,H,W", [(20, 2, 8, 12), (27, 1, 16, 32), (20, 1, 33, 65), (32, 1, 6, 70), (20, 2, 5, 130),
+                                         (2, 1, 4, 64)])
 def test_output_conv(ccls, N, H, W):
     import torch.nn.functional as F
     from mdil_ss_b200.functional import OutConvFn
@@ -227,6 +230,31 @@ def test_output_conv(ccls, N, H, W):
     assert_close(xd.grad, x.grad, TOL, "dx")
     assert_close(wd.grad, w.grad, TOL, "dw")
     assert_close(bd.grad, b.grad, TOL, "db")
+
+
+@pytest.mark.parametrize("c,N,H,W", [(20, 2, 16, 32), (27, 1, 9, 13), (5, 3, 7, 10), (32, 1, 4, 6)])
+def test_cross_entropy2d_two_phase(c, N, H, W):
+    """CrossEntropyLoss2d (train_new_task_step2.py:84-92) against torch's NLLLoss(log_softmax): loss-only forward, gradient
+    recomputed in the backward pass and scaled by an upstream factor; odd H*W (scalar path) and an ignored class (weight
+    0) included; a second backward through a retained graph gives the same gradient."""
+    import torch.nn.functional as F
+    from mdil_ss_b200.losses import CrossEntropyLoss2d
+    g = torch.Generator().manual_seed(40 + c)
+    logits = (3.0 * torch.randn(N, c, H, W, generator=g)).requires_grad_(True)
+    labels = torch.randint(0, c, (N, H, W), generator=g)
+    wts = torch.rand(c, generator=g) + 0.1
+    wts[c - 1] = 0.0
+    ref = F.nll_loss(F.log_softmax(logits, 1), labels, wts)
+    (2.5 * ref).backward()
+    ld = logits.detach().to(DEV).requires_grad_(True)
+    loss = CrossEntropyLoss2d(wts).to(DEV)(ld, labels.to(DEV))
+    assert abs(float(loss.detach()) - float(ref.detach())) <= 1e-5 * abs(float(ref.detach()))
+    (2.5 * loss).backward(retain_graph=True)
+    assert_close(ld.grad, logits.grad, 1e-4, "dlogits")
+    first = ld.grad.clone()
+    ld.grad = None
+    (2.5 * loss).backward()
+    assert torch.equal(ld.grad, first)
 
 
 def test_cpu_tensor_is_rejected():

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libmdil_b200.so")
-SOURCES = ["elementwise.cu", "conv_taps.cu", "nb1d_pair.cu", "nb1d_pair_tc3.cu", "nb1d_pair_h3.cu", "wgrad_tc.cu", "head_loss.cu", "cotransform.cu", "api.cu"]
+SOURCES = ["elementwise.cu", "conv_taps.cu", "nb1d_pair.cu", "nb1d_pair_tc3.cu", "nb1d_pair_h3.cu", "wgrad_tc.cu", "conv_tc.cu", "head_loss.cu", "cotransform.cu", "api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]          # no --use_fast_math: fp32 parity with the reference
 

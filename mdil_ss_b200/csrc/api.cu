@@ -511,8 +511,24 @@ static inline int down_cinp(const mdil_down_desc* d) { return d->ldin; }
 static inline int down_cconv(const mdil_down_desc* d) { return d->Cout - d->Cin; }
 static inline int down_coutp(const mdil_down_desc* d) { return (down_cconv(d) + 3) / 4 * 4; }
 
-size_t mdil_down_packed_floats(const mdil_down_desc* d) {
+static size_t down_slab_floats(const mdil_down_desc* d) {
   return (size_t)9 * down_cinp(d) * down_coutp(d) + (size_t)9 * down_cconv(d) * d->Cin + 64;
+}
+// data gradient of the strided conv = a parity-class transposed conv from du (first Cc channels) to dx
+static ConvGeom down_dgrad_geom(const mdil_down_desc* d) {
+  const int OH = d->H / 2, OW = d->W / 2, Cc = down_cconv(d);
+  ConvGeom g;
+  memset(&g, 0, sizeof(g));
+  g.N = d->N; g.VH = OH; g.VW = OW;
+  g.AH = OH; g.AW = OW; g.lda = d->Cout; g.a_coff = 0; g.a_sy = 1; g.a_sx = 1;
+  g.GH = d->H; g.GW = d->W; g.ldg = d->Cin; g.g_coff = 0; g.g_sy = 2; g.g_sx = 2;
+  g.CIN = Cc; g.COUT = d->Cin; g.COUT_PAD = d->Cin; g.CIN_VALID = Cc;
+  fill_parity_classes(g);
+  return g;
+}
+// [fp32 tap slabs of the forward conv and of the data gradient][16-bit chunk images of the tensor-core data gradient]
+size_t mdil_down_packed_floats(const mdil_down_desc* d) {
+  return down_slab_floats(d) + conv_tc_image_floats(down_cconv(d), d->Cin);
 }
 
 size_t mdil_down_workspace_bytes(const mdil_down_desc* d) {
@@ -535,14 +551,20 @@ int mdil_down_pack(const mdil_down_desc* d, const float* w, float* packed, void*
   // forward: slab[t][ci][co] = W[co][ci][t]
   MDIL_TRY(launch_pack(w, packed, 9, Cin, CinP, Cc, CoP, 9, 9L * Cin, 1, 0, s));
   // dgrad: slab[t][co][ci] = W[co][ci][t]
-  if (Cin % 4 == 0 && Cc % 4 == 0)
+  if (Cin % 4 == 0 && Cc % 4 == 0) {
     MDIL_TRY(launch_pack(w, packed + (size_t)9 * CinP * CoP, 9, Cc, Cc, Cin, Cin, 9L * Cin, 9, 1, 0, s));
+    if (d->ldin == Cin) {
+      const ConvGeom g = down_dgrad_geom(d);
+      if (conv_tc_ok(g, 1))
+        MDIL_TRY(launch_pack_conv_tc(g, packed + (size_t)9 * CinP * CoP, packed + down_slab_floats(d), 1, s));
+    }
+  }
   return 0;
 }
 
 static int bn_forward_tail(const float* u, size_t P, int C, const mdil_bn_params* bn, int train, float eps, float momentum,
-                           double* sums, float* stats, float* y, int N, size_t HW, cudaStream_t s) {
-  if (train) {
+                           double* sums, float* stats, float* y, int N, size_t HW, cudaStream_t s, bool have_sums = false) {
+  if (train && !have_sums) {     // have_sums: the producing kernel's epilogue accumulated them
     MDIL_CUDA(cudaMemsetAsync(sums, 0, 2 * C * sizeof(double), s));
     MDIL_TRY(launch_channel_stats(u, P, C, 0, C, sums, C, s));
   }
@@ -608,21 +630,18 @@ int mdil_down_bwd(const mdil_down_desc* d, const float* dy, const float* x, cons
   }
   if (dx != nullptr) {
     MDIL_REQUIRE(Cin % 4 == 0 && Cc % 4 == 0 && d->ldin == Cin, "down_bwd: dx needs Cin % 4 == 0");
-    ConvGeom g;
-    memset(&g, 0, sizeof(g));
-    g.N = d->N; g.VH = OH; g.VW = OW;
-    g.AH = OH; g.AW = OW; g.lda = Cout; g.a_coff = 0; g.a_sy = 1; g.a_sx = 1;
-    g.GH = d->H; g.GW = d->W; g.ldg = Cin; g.g_coff = 0; g.g_sy = 2; g.g_sx = 2;
-    g.CIN = Cc; g.COUT = Cin; g.COUT_PAD = Cin; g.CIN_VALID = Cc;
-    fill_parity_classes(g);
-    MDIL_TRY(launch_conv_taps(g, du, packed + (size_t)9 * down_cinp(d) * down_coutp(d), nullptr, dx, s));
+    const ConvGeom g = down_dgrad_geom(d);
+    if (conv_tc_ok(g, 1)) MDIL_TRY(launch_conv_tc(g, du, packed + down_slab_floats(d), nullptr, dx, nullptr, 1, s));
+    else MDIL_TRY(launch_conv_taps(g, du, packed + (size_t)9 * down_cinp(d) * down_coutp(d), nullptr, dx, s));
     MDIL_TRY(launch_pool_bwd(x, du, dx, d->N, d->H, d->W, Cin, d->ldin, Cout, Cc, 1, s));
   }
   return 0;
 }
 
 // =============================================================================== upsampler
-size_t mdil_up_packed_floats(const mdil_up_desc* d) { return (size_t)18 * d->Cin * d->Cout + 64; }
+static size_t up_slab_floats(const mdil_up_desc* d) { return (size_t)18 * d->Cin * d->Cout + 64; }
+// [fp32 tap slabs of the forward conv and of the data gradient][16-bit chunk images of the tensor-core forward conv]
+size_t mdil_up_packed_floats(const mdil_up_desc* d) { return up_slab_floats(d) + conv_tc_image_floats(d->Cin, d->Cout); }
 
 size_t mdil_up_workspace_bytes(const mdil_up_desc* d) {
   size_t du = align_up((size_t)d->N * (2 * d->H) * (2 * d->W) * d->Cout * sizeof(float), 256);
@@ -633,17 +652,6 @@ size_t mdil_up_workspace_bytes(const mdil_up_desc* d) {
 static int check_up(const mdil_up_desc* d) {
   MDIL_REQUIRE(d != nullptr && d->N > 0 && d->H > 0 && d->W > 0, "up: bad dims");
   MDIL_REQUIRE(d->Cin % 4 == 0 && d->Cout % 4 == 0 && 256 % (d->Cout / 4) == 0, "up: bad channels");
-  return 0;
-}
-
-int mdil_up_pack(const mdil_up_desc* d, const float* w, float* packed, void* stream) {
-  MDIL_TRY(check_up(d));
-  const int Cin = d->Cin, Cout = d->Cout;
-  cudaStream_t s = S(stream);
-  // forward: slab[t][ci][co] = W[ci][co][t]   (torch ConvTranspose2d layout [Cin][Cout][3][3])
-  MDIL_TRY(launch_pack(w, packed, 9, Cin, Cin, Cout, Cout, 9L * Cout, 9, 1, 0, s));
-  // dgrad: slab[t][co][ci] = W[ci][co][t]
-  MDIL_TRY(launch_pack(w, packed + (size_t)9 * Cin * Cout, 9, Cout, Cout, Cin, Cin, 9, 9L * Cout, 1, 0, s));
   return 0;
 }
 
@@ -658,17 +666,36 @@ static ConvGeom up_parity_geom(const mdil_up_desc* d) {
   return g;
 }
 
+int mdil_up_pack(const mdil_up_desc* d, const float* w, float* packed, void* stream) {
+  MDIL_TRY(check_up(d));
+  const int Cin = d->Cin, Cout = d->Cout;
+  cudaStream_t s = S(stream);
+  // forward: slab[t][ci][co] = W[ci][co][t]   (torch ConvTranspose2d layout [Cin][Cout][3][3])
+  MDIL_TRY(launch_pack(w, packed, 9, Cin, Cin, Cout, Cout, 9L * Cout, 9, 1, 0, s));
+  // dgrad: slab[t][co][ci] = W[ci][co][t]
+  MDIL_TRY(launch_pack(w, packed + (size_t)9 * Cin * Cout, 9, Cout, Cout, Cin, Cin, 9, 9L * Cout, 1, 0, s));
+  const ConvGeom g = up_parity_geom(d);
+  if (conv_tc_ok(g, 0)) MDIL_TRY(launch_pack_conv_tc(g, packed, packed + up_slab_floats(d), 0, s));
+  return 0;
+}
+
 int mdil_up_fwd(const mdil_up_desc* d, const float* x, const float* packed, const float* bias, const mdil_bn_params* bn,
                 float* u, float* stats, float* y, void* ws, size_t ws_bytes, void* stream) {
   MDIL_TRY(check_up(d));
   MDIL_REQUIRE(ws_bytes >= (size_t)2 * d->Cout * sizeof(double) + 512, "up_fwd: workspace too small");
   cudaStream_t s = S(stream);
   ConvGeom g = up_parity_geom(d);
-  MDIL_TRY(launch_conv_taps(g, x, packed, bias, u, s));
   Carver cv(ws);
   double* sums = cv.take<double>(2 * d->Cout);
   const size_t OHW = (size_t)4 * d->H * d->W;
-  return bn_forward_tail(u, (size_t)d->N * OHW, d->Cout, bn, d->train, d->eps, d->momentum, sums, stats, y, d->N, OHW, s);
+  const bool tc = conv_tc_ok(g, 0);
+  if (tc) {     // tensor-core kernel; its epilogue accumulates the BatchNorm sums of u
+    if (d->train) MDIL_CUDA(cudaMemsetAsync(sums, 0, 2 * d->Cout * sizeof(double), s));
+    MDIL_TRY(launch_conv_tc(g, x, packed + up_slab_floats(d), bias, u, d->train ? sums : nullptr, 0, s));
+  } else {
+    MDIL_TRY(launch_conv_taps(g, x, packed, bias, u, s));
+  }
+  return bn_forward_tail(u, (size_t)d->N * OHW, d->Cout, bn, d->train, d->eps, d->momentum, sums, stats, y, d->N, OHW, s, tc);
 }
 
 int mdil_up_bwd(const mdil_up_desc* d, const float* dy, const float* x, const float* u, const float* y,

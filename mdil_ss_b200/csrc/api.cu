@@ -512,7 +512,18 @@ static inline int down_cconv(const mdil_down_desc* d) { return d->Cout - d->Cin;
 static inline int down_coutp(const mdil_down_desc* d) { return (down_cconv(d) + 3) / 4 * 4; }
 
 static size_t down_slab_floats(const mdil_down_desc* d) {
-  return (size_t)9 * down_cinp(d) * down_coutp(d) + (size_t)9 * down_cconv(d) * d->Cin + 64;
+  return ((size_t)9 * down_cinp(d) * down_coutp(d) + (size_t)9 * down_cconv(d) * d->Cin + 64 + 3) / 4 * 4;   // images: 16-byte aligned
+}
+static ConvGeom down_fwd_geom(const mdil_down_desc* d) {
+  const int OH = d->H / 2, OW = d->W / 2;
+  ConvGeom g;
+  memset(&g, 0, sizeof(g));
+  g.N = d->N; g.VH = OH; g.VW = OW;
+  g.AH = d->H; g.AW = d->W; g.lda = d->ldin; g.a_coff = 0; g.a_sy = 2; g.a_sx = 2;
+  g.GH = OH; g.GW = OW; g.ldg = d->Cout; g.g_coff = 0; g.g_sy = 1; g.g_sx = 1;
+  g.CIN = down_cinp(d); g.COUT = down_cconv(d); g.COUT_PAD = down_coutp(d); g.CIN_VALID = d->Cin;
+  fill_3x3_taps(g);
+  return g;
 }
 // data gradient of the strided conv = a parity-class transposed conv from du (first Cc channels) to dx
 static ConvGeom down_dgrad_geom(const mdil_down_desc* d) {
@@ -526,9 +537,11 @@ static ConvGeom down_dgrad_geom(const mdil_down_desc* d) {
   fill_parity_classes(g);
   return g;
 }
-// [fp32 tap slabs of the forward conv and of the data gradient][16-bit chunk images of the tensor-core data gradient]
+// [fp32 tap slabs of the forward conv and of the data gradient][16-bit chunk images of the tensor-core kernel: forward,
+// data gradient]
+static size_t down_img_fwd_floats(const mdil_down_desc* d) { return conv_tc_image_floats(down_cinp(d), down_coutp(d)); }
 size_t mdil_down_packed_floats(const mdil_down_desc* d) {
-  return down_slab_floats(d) + conv_tc_image_floats(down_cconv(d), d->Cin);
+  return down_slab_floats(d) + down_img_fwd_floats(d) + conv_tc_image_floats(down_cconv(d), d->Cin);
 }
 
 size_t mdil_down_workspace_bytes(const mdil_down_desc* d) {
@@ -556,9 +569,11 @@ int mdil_down_pack(const mdil_down_desc* d, const float* w, float* packed, void*
     if (d->ldin == Cin) {
       const ConvGeom g = down_dgrad_geom(d);
       if (conv_tc_ok(g, 1))
-        MDIL_TRY(launch_pack_conv_tc(g, packed + (size_t)9 * CinP * CoP, packed + down_slab_floats(d), 1, s));
+        MDIL_TRY(launch_pack_conv_tc(g, packed + (size_t)9 * CinP * CoP, Cc, packed + down_slab_floats(d) + down_img_fwd_floats(d), 1, s));
     }
   }
+  const ConvGeom gf = down_fwd_geom(d);
+  if (conv_tc_ok(gf, 0)) MDIL_TRY(launch_pack_conv_tc(gf, packed, CinP, packed + down_slab_floats(d), 0, s));
   return 0;
 }
 
@@ -578,14 +593,9 @@ int mdil_down_fwd(const mdil_down_desc* d, const float* x, const float* packed, 
   MDIL_REQUIRE(ws_bytes >= (size_t)2 * d->Cout * sizeof(double) + 512, "down_fwd: workspace too small");
   cudaStream_t s = S(stream);
   const int OH = d->H / 2, OW = d->W / 2, Cc = down_cconv(d);
-  ConvGeom g;
-  memset(&g, 0, sizeof(g));
-  g.N = d->N; g.VH = OH; g.VW = OW;
-  g.AH = d->H; g.AW = d->W; g.lda = d->ldin; g.a_coff = 0; g.a_sy = 2; g.a_sx = 2;
-  g.GH = OH; g.GW = OW; g.ldg = d->Cout; g.g_coff = 0; g.g_sy = 1; g.g_sx = 1;
-  g.CIN = down_cinp(d); g.COUT = Cc; g.COUT_PAD = down_coutp(d); g.CIN_VALID = d->Cin;
-  fill_3x3_taps(g);
-  MDIL_TRY(launch_conv_taps(g, x, packed, bias, u, s));
+  const ConvGeom g = down_fwd_geom(d);
+  if (conv_tc_ok(g, 0)) MDIL_TRY(launch_conv_tc(g, x, packed + down_slab_floats(d), bias, u, nullptr, 0, s));
+  else MDIL_TRY(launch_conv_taps(g, x, packed, bias, u, s));
   MDIL_TRY(launch_pool_fwd(x, u, d->N, d->H, d->W, d->Cin, d->ldin, d->Cout, Cc, s));
   Carver cv(ws);
   double* sums = cv.take<double>(2 * d->Cout);
@@ -631,7 +641,8 @@ int mdil_down_bwd(const mdil_down_desc* d, const float* dy, const float* x, cons
   if (dx != nullptr) {
     MDIL_REQUIRE(Cin % 4 == 0 && Cc % 4 == 0 && d->ldin == Cin, "down_bwd: dx needs Cin % 4 == 0");
     const ConvGeom g = down_dgrad_geom(d);
-    if (conv_tc_ok(g, 1)) MDIL_TRY(launch_conv_tc(g, du, packed + down_slab_floats(d), nullptr, dx, nullptr, 1, s));
+    if (conv_tc_ok(g, 1))
+      MDIL_TRY(launch_conv_tc(g, du, packed + down_slab_floats(d) + down_img_fwd_floats(d), nullptr, dx, nullptr, 1, s));
     else MDIL_TRY(launch_conv_taps(g, du, packed + (size_t)9 * down_cinp(d) * down_coutp(d), nullptr, dx, s));
     MDIL_TRY(launch_pool_bwd(x, du, dx, d->N, d->H, d->W, Cin, d->ldin, Cout, Cc, 1, s));
   }
@@ -640,8 +651,23 @@ int mdil_down_bwd(const mdil_down_desc* d, const float* dy, const float* x, cons
 
 // =============================================================================== upsampler
 static size_t up_slab_floats(const mdil_up_desc* d) { return (size_t)18 * d->Cin * d->Cout + 64; }
-// [fp32 tap slabs of the forward conv and of the data gradient][16-bit chunk images of the tensor-core forward conv]
-size_t mdil_up_packed_floats(const mdil_up_desc* d) { return up_slab_floats(d) + conv_tc_image_floats(d->Cin, d->Cout); }
+static size_t up_img_fwd_floats(const mdil_up_desc* d) { return conv_tc_image_floats(d->Cin, d->Cout); }
+// [fp32 tap slabs of the forward conv and of the data gradient][16-bit chunk images of the tensor-core kernel: forward,
+// data gradient]
+size_t mdil_up_packed_floats(const mdil_up_desc* d) {
+  return up_slab_floats(d) + up_img_fwd_floats(d) + conv_tc_image_floats(d->Cout, d->Cin);
+}
+// data gradient of the transposed conv = a strided 3x3 conv from du to dx
+static ConvGeom up_dgrad_geom(const mdil_up_desc* d) {
+  ConvGeom g;
+  memset(&g, 0, sizeof(g));
+  g.N = d->N; g.VH = d->H; g.VW = d->W;
+  g.AH = 2 * d->H; g.AW = 2 * d->W; g.lda = d->Cout; g.a_coff = 0; g.a_sy = 2; g.a_sx = 2;
+  g.GH = d->H; g.GW = d->W; g.ldg = d->Cin; g.g_coff = 0; g.g_sy = 1; g.g_sx = 1;
+  g.CIN = d->Cout; g.COUT = d->Cin; g.COUT_PAD = d->Cin; g.CIN_VALID = d->Cout;
+  fill_3x3_taps(g);
+  return g;
+}
 
 size_t mdil_up_workspace_bytes(const mdil_up_desc* d) {
   size_t du = align_up((size_t)d->N * (2 * d->H) * (2 * d->W) * d->Cout * sizeof(float), 256);
@@ -675,7 +701,10 @@ int mdil_up_pack(const mdil_up_desc* d, const float* w, float* packed, void* str
   // dgrad: slab[t][co][ci] = W[ci][co][t]
   MDIL_TRY(launch_pack(w, packed + (size_t)9 * Cin * Cout, 9, Cout, Cout, Cin, Cin, 9, 9L * Cout, 1, 0, s));
   const ConvGeom g = up_parity_geom(d);
-  if (conv_tc_ok(g, 0)) MDIL_TRY(launch_pack_conv_tc(g, packed, packed + up_slab_floats(d), 0, s));
+  if (conv_tc_ok(g, 0)) MDIL_TRY(launch_pack_conv_tc(g, packed, Cin, packed + up_slab_floats(d), 0, s));
+  const ConvGeom gd = up_dgrad_geom(d);
+  if (conv_tc_ok(gd, 1))
+    MDIL_TRY(launch_pack_conv_tc(gd, packed + (size_t)9 * Cin * Cout, Cout, packed + up_slab_floats(d) + up_img_fwd_floats(d), 1, s));
   return 0;
 }
 
@@ -728,14 +757,11 @@ int mdil_up_bwd(const mdil_up_desc* d, const float* dy, const float* x, const fl
     MDIL_REQUIRE(db == nullptr, "up_bwd: bias gradient without weight gradient is not supported");
   }
   if (dx != nullptr) {
-    ConvGeom g;
-    memset(&g, 0, sizeof(g));
-    g.N = d->N; g.VH = d->H; g.VW = d->W;
-    g.AH = 2 * d->H; g.AW = 2 * d->W; g.lda = Cout; g.a_coff = 0; g.a_sy = 2; g.a_sx = 2;
-    g.GH = d->H; g.GW = d->W; g.ldg = Cin; g.g_coff = 0; g.g_sy = 1; g.g_sx = 1;
-    g.CIN = Cout; g.COUT = Cin; g.COUT_PAD = Cin; g.CIN_VALID = Cout;
-    fill_3x3_taps(g);
-    MDIL_TRY(launch_conv_taps(g, du, packed + (size_t)9 * Cin * Cout, nullptr, dx, s));
+    const ConvGeom g = up_dgrad_geom(d);
+    if (conv_tc_ok(g, 1))
+      MDIL_TRY(launch_conv_tc(g, du, packed + up_slab_floats(d) + up_img_fwd_floats(d), nullptr, dx, nullptr, 1, s));
+    else
+      MDIL_TRY(launch_conv_taps(g, du, packed + (size_t)9 * Cin * Cout, nullptr, dx, s));
   }
   return 0;
 }

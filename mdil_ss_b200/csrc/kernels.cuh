@@ -96,13 +96,14 @@ int launch_pack(const float* src, float* dst, int T, int A, int Apad, int B, int
                 cudaStream_t s);
 
 // ---------------------------------------------------------------- conv_tc.cu
-// parity-class (sub-pixel) 3x3 stride-2 transposed convolution on tcgen05: UpsamplerBlock forward (grad = 0: CIN 128 -> 64,
-// 64 -> 16, fp16 split operands) and the data gradient of DownsamplerBlock's 64 -> 64 convolution (grad = 1, bf16 split).
-// wimg: 16-bit hi/lo chunk images built by launch_pack_conv_tc from the fp32 tap slabs Wp[widx][CIN][COUT_PAD];
-// sums (nullable): [2][COUT] fp64 sum / sum of squares of the output (zeroed by the caller)
+// The samplers' 3x3 stride-2 convolutions on tcgen05 (fp16 split operands forward, bf16 for gradients): the parity-class
+// transposed form (UpsamplerBlock forward, DownsamplerBlock data gradient) and the strided form (DownsamplerBlock forward,
+// UpsamplerBlock data gradient) of a ConvGeom.  wimg: 16-bit hi/lo chunk images built by launch_pack_conv_tc from the
+// fp32 tap slabs Wp[widx][wp_rows][COUT_PAD] (conv_tc_image_floats(CIN, COUT_PAD) floats);
+// sums (nullable, transposed form only): [2][COUT] fp64 sum / sum of squares of the output (zeroed by the caller)
 bool conv_tc_ok(const ConvGeom& g, int grad);
-size_t conv_tc_image_floats(int cin, int cout);
-int launch_pack_conv_tc(const ConvGeom& g, const float* Wp, void* img, int grad, cudaStream_t s);
+size_t conv_tc_image_floats(int cin, int cout_pad);
+int launch_pack_conv_tc(const ConvGeom& g, const float* Wp, int wp_rows, void* img, int grad, cudaStream_t s);
 int launch_conv_tc(const ConvGeom& g, const float* A, const void* wimg, const float* bias, float* out, double* sums, int grad,
                    cudaStream_t s);
 

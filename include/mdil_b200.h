@@ -59,6 +59,7 @@ typedef struct {
   const float* bias;     /* beta  [C] */
   float* running_mean;   /* [C], updated in place when train != 0 */
   float* running_var;    /* [C] */
+  long long* num_batches_tracked; /* nullable device scalar (nn.BatchNorm2d's buffer): += 1 by a train-mode forward launch */
 } mdil_bn_params;
 
 /* ------------------------------------------------------------- nb1d block */

@@ -29,7 +29,7 @@ EXPORTS = [
 
 class BnParams(C.Structure):
     _fields_ = [("weight", C.c_void_p), ("bias", C.c_void_p), ("running_mean", C.c_void_p),
-                ("running_var", C.c_void_p)]
+                ("running_var", C.c_void_p), ("num_batches_tracked", C.c_void_p)]
 
 
 class Nb1dDesc(C.Structure):

@@ -255,14 +255,14 @@ static int nb1d_fwd_p4(const mdil_nb1d_desc* d, const float* x, const mdil_nb1d_
   }
   MDIL_TRY(launch_pair(a, s));
   MDIL_TRY(launch_bn_finalize(sums1, CP, count, C, w->bn1.weight, w->bn1.bias, w->bn1.running_mean, w->bn1.running_var,
-                              d->eps, d->momentum, d->train, st1, s, 4, rep1));
+                              d->eps, d->momentum, d->train, st1, s, 4, rep1, w->bn1.num_batches_tracked));
   a.in = sv->p; a.in_scale = rep1 + 2 * CP; a.in_shift = rep1 + 3 * CP; a.wstream_tc = p4_stream(packed, 1);
   a.b1 = p4_bias(packed, 2); a.b2 = p4_bias(packed, 3);
   a.mid_out = d->save ? sv->c : nullptr; a.out = sv->s; a.sums = d->train ? sums2 : nullptr;
   MDIL_TRY(launch_pair(a, s));
   // y = relu(bn2(s) * drop + x), the BatchNorm finalisation in the same launch
   return launch_bn_act_fused(sv->s, sums2, CP, count, w->bn2.weight, w->bn2.bias, w->bn2.running_mean, w->bn2.running_var,
-                             d->eps, d->momentum, d->train, 4, st2, drop_mask, x, y, d->N, HW, C, s);
+                             d->eps, d->momentum, d->train, 4, st2, drop_mask, x, y, d->N, HW, C, s, w->bn2.num_batches_tracked);
 }
 
 int mdil_nb1d_fwd(const mdil_nb1d_desc* d, const float* x, const mdil_nb1d_weights* w, const float* packed,
@@ -304,7 +304,7 @@ int mdil_nb1d_fwd(const mdil_nb1d_desc* d, const float* x, const mdil_nb1d_weigh
   }
   MDIL_TRY(launch_pair(a, s));
   MDIL_TRY(launch_bn_finalize(sums1, C, count, C, w->bn1.weight, w->bn1.bias, w->bn1.running_mean, w->bn1.running_var,
-                              d->eps, d->momentum, d->train, st1, s));
+                              d->eps, d->momentum, d->train, st1, s, 1, nullptr, w->bn1.num_batches_tracked));
   // pair 2: r = relu(bn1(p)) -> c -> s
   a.in = sv->p; a.in_scale = st1 + 2 * C; a.in_shift = st1 + 3 * C; a.wstream = packed + 7 * CC; a.wstream_tc = tc_stream(packed, C, 1);
   a.b1 = w->b31_2; a.b2 = w->b13_2; a.bad = d->has_adapter ? w->bp2 : nullptr;
@@ -312,7 +312,7 @@ int mdil_nb1d_fwd(const mdil_nb1d_desc* d, const float* x, const mdil_nb1d_weigh
   MDIL_TRY(launch_pair(a, s));
   // y = relu(bn2(s) * drop + x), the BatchNorm finalisation in the same launch
   return launch_bn_act_fused(sv->s, sums2, C, count, w->bn2.weight, w->bn2.bias, w->bn2.running_mean, w->bn2.running_var,
-                             d->eps, d->momentum, d->train, 1, st2, drop_mask, x, y, d->N, HW, C, s);
+                             d->eps, d->momentum, d->train, 1, st2, drop_mask, x, y, d->N, HW, C, s, w->bn2.num_batches_tracked);
 }
 
 // One weight gradient of the block: tensor-core path (C = 64, 128) or the generic FFMA tap kernel.
@@ -584,7 +584,7 @@ static int bn_forward_tail(const float* u, size_t P, int C, const mdil_bn_params
     MDIL_TRY(launch_channel_stats(u, P, C, 0, C, sums, C, s));
   }
   return launch_bn_act_fused(u, sums, C, (double)P, bn->weight, bn->bias, bn->running_mean, bn->running_var, eps, momentum,
-                             train, 1, stats, nullptr, nullptr, y, N, HW, C, s);
+                             train, 1, stats, nullptr, nullptr, y, N, HW, C, s, bn->num_batches_tracked);
 }
 
 int mdil_down_fwd(const mdil_down_desc* d, const float* x, const float* packed, const float* bias,

@@ -122,8 +122,9 @@ int launch_bn_bwd_stats(const float* dy, const float* y, const float* drop, cons
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, int ldsum, double count, int C,
                                    const float* __restrict__ gamma, const float* __restrict__ beta, float* rm, float* rv,
                                    float eps, float momentum, int train, float* __restrict__ stats, int fold,
-                                   float* __restrict__ stats_rep) {
+                                   float* __restrict__ stats_rep, long long* nbt) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && train && nbt != nullptr) *nbt += 1;      // nn.BatchNorm2d.num_batches_tracked
   if (c >= C) return;
   float mean, var;
   if (train) {
@@ -161,9 +162,9 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, int ldsum, d
 
 int launch_bn_finalize(const double* sums, int ldsum, double count, int C, const float* gamma, const float* beta,
                        float* rm, float* rv, float eps, float momentum, int train, float* stats, cudaStream_t s,
-                       int fold, float* stats_rep) {
+                       int fold, float* stats_rep, long long* nbt) {
   bn_finalize_kernel<<<cdiv(C, 128), 128, 0, s>>>(sums, ldsum, count, C, gamma, beta, rm, rv, eps, momentum, train, stats,
-                                                  fold, stats_rep);
+                                                  fold, stats_rep, nbt);
   MDIL_LAUNCH_CHECK();
   return 0;
 }
@@ -210,8 +211,9 @@ __global__ void __launch_bounds__(256)
 bn_act_fused_kernel(const float* __restrict__ u, const double* __restrict__ sums, int ldsum, double count,
                     const float* __restrict__ gamma, const float* __restrict__ beta, float* rm, float* rv, float eps,
                     float momentum, int train, int fold, float* __restrict__ stats, const float* __restrict__ drop,
-                    const float* __restrict__ res, float* __restrict__ y, size_t total4, size_t HWC4, int C) {
+                    const float* __restrict__ res, float* __restrict__ y, size_t total4, size_t HWC4, int C, long long* nbt) {
   __shared__ __align__(16) float cf[2 * 128];      // scale, shift
+  if (blockIdx.x == 0 && threadIdx.x == 0 && train && nbt != nullptr) *nbt += 1;      // nn.BatchNorm2d.num_batches_tracked
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float mean, var;
     double unbiased = 0.0;
@@ -266,11 +268,11 @@ bn_act_fused_kernel(const float* __restrict__ u, const double* __restrict__ sums
 
 int launch_bn_act_fused(const float* u, const double* sums, int ldsum, double count, const float* gamma, const float* beta,
                         float* rm, float* rv, float eps, float momentum, int train, int fold, float* stats, const float* drop,
-                        const float* res, float* y, int N, size_t HW, int C, cudaStream_t s) {
+                        const float* res, float* y, int N, size_t HW, int C, cudaStream_t s, long long* nbt) {
   MDIL_REQUIRE(C % 4 == 0 && C <= 128, "bn_act_fused: C % 4, C <= 128");
   size_t total4 = (size_t)N * HW * (C / 4);
   bn_act_fused_kernel<<<ew_grid(total4, 256), 256, 0, s>>>(u, sums, ldsum, count, gamma, beta, rm, rv, eps, momentum, train, fold,
-                                                           stats, drop, res, y, total4, HW * (C / 4), C);
+                                                           stats, drop, res, y, total4, HW * (C / 4), C, nbt);
   MDIL_LAUNCH_CHECK();
   return 0;
 }

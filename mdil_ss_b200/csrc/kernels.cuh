@@ -16,7 +16,7 @@ int launch_channel_stats(const float* x, size_t P, int ld, int coff, int cnt, do
 // fold*C); stats_rep (nullable) [4][fold*C] receives the statistics replicated per slot.
 int launch_bn_finalize(const double* sums, int ldsum, double count, int C, const float* gamma, const float* beta,
                        float* running_mean, float* running_var, float eps, float momentum, int train, float* stats,
-                       cudaStream_t s, int fold = 1, float* stats_rep = nullptr);
+                       cudaStream_t s, int fold = 1, float* stats_rep = nullptr, long long* nbt = nullptr);
 
 // y = relu((u*scale+shift) * drop[n][c] + res)   (drop, res nullable)
 int launch_bn_act(const float* u, const float* stats, const float* drop, const float* res, float* y, int N, size_t HW,
@@ -35,7 +35,7 @@ int launch_bn_bwd_finalize(const double* sums, double count, int C, const float*
 // launch_bn_finalize + launch_bn_act in one launch (C <= 128; no replicated statistics)
 int launch_bn_act_fused(const float* u, const double* sums, int ldsum, double count, const float* gamma, const float* beta,
                         float* rm, float* rv, float eps, float momentum, int train, int fold, float* stats, const float* drop,
-                        const float* res, float* y, int N, size_t HW, int C, cudaStream_t s);
+                        const float* res, float* y, int N, size_t HW, int C, cudaStream_t s, long long* nbt = nullptr);
 // launch_bn_bwd_finalize + launch_bn_bwd_apply in one launch (C <= 128)
 int launch_bn_bwd_apply_fused(const float* dy, const float* y, const float* drop, const float* u, const float* stats,
                               const double* sums, double count, const float* gamma, int fold, float* dgamma, float* dbeta,

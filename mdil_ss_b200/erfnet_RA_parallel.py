@@ -22,12 +22,8 @@ current_task = 0
 
 
 def _bn_buffers(bn: nn.BatchNorm2d):
-    return (bn.running_mean, bn.running_var)
-
-
-def _tick(bn: nn.BatchNorm2d, training: bool) -> None:
-    if training and bn.num_batches_tracked is not None:
-        bn.num_batches_tracked.add_(1)
+    # running statistics and the batch counter: all three are updated by the train-mode forward launch itself
+    return (bn.running_mean, bn.running_var, bn.num_batches_tracked)
 
 
 class DownsamplerBlock(nn.Module):
@@ -43,7 +39,6 @@ class DownsamplerBlock(nn.Module):
         bn = self.bn_ini[task]
         cfg = F_.SampConfig(self.training, _bn_buffers(bn), self._cache, 0)
         out = F_.DownFn.apply(input, cfg, self.conv.weight, self.conv.bias, bn.weight, bn.bias)
-        _tick(bn, self.training)
         return out
 
 
@@ -77,8 +72,6 @@ class non_bottleneck_1d(nn.Module):
                               self.conv3x1_1.weight, self.conv3x1_1.bias, self.conv1x3_1.weight, self.conv1x3_1.bias,
                               self.conv3x1_2.weight, self.conv3x1_2.bias, self.conv1x3_2.weight, self.conv1x3_2.bias,
                               self.bn1.weight, self.bn1.bias, self.bn2.weight, self.bn2.bias)
-        _tick(self.bn1, self.training)
-        _tick(self.bn2, self.training)
         return out
 
 
@@ -115,8 +108,6 @@ class non_bottleneck_1d_RAP(nn.Module):
                               self.conv3x1_2.weight, self.conv3x1_2.bias, self.conv1x3_2.weight, self.conv1x3_2.bias,
                               bn1.weight, bn1.bias, bn2.weight, bn2.bias,
                               ad1.weight, ad1.bias, ad2.weight, ad2.bias)
-        _tick(bn1, self.training)
-        _tick(bn2, self.training)
         return out
 
 
@@ -135,9 +126,37 @@ class Encoder(nn.Module):
             self.layers.append(non_bottleneck_1d_RAP(128, 0.3, 8, nb_tasks))
             self.layers.append(non_bottleneck_1d_RAP(128, 0.3, 16, nb_tasks))
 
+    def _draw_noise(self, n, device):
+        """The Dropout2d noise of every block of one training forward from ONE uniform draw ([N, C, 1, 1] per layer,
+        bernoulli(1 - p) / (1 - p) like F.dropout2d): three small launches instead of two per block."""
+        key = (n, str(device))
+        plan = getattr(self, "_noise_plan", None)
+        if plan is None or plan[0] != key:
+            spans, keep = [], []
+            off = 0
+            for i, layer in enumerate(self.layers):
+                if isinstance(layer, non_bottleneck_1d_RAP) and layer.dropout.p > 0:
+                    c = layer.bns_1[0].num_features
+                    spans.append((i, off, c))
+                    keep += [1.0 - layer.dropout.p] * (n * c)
+                    off += n * c
+            keep_t = torch.tensor(keep, dtype=torch.float32, device=device)
+            plan = (key, spans, keep_t, 1.0 / keep_t, off)
+            self._noise_plan = plan
+        _, spans, keep_t, inv_t, total = plan
+        noise = [None] * len(self.layers)
+        if total == 0:
+            return noise
+        flat = (torch.rand(total, device=device) < keep_t).to(torch.float32) * inv_t
+        for i, off, c in spans:
+            noise[i] = flat[off:off + n * c].view(n, c, 1, 1)
+        return noise
+
     def forward(self, input, predict=False, drop_noise=None):
         """``drop_noise``: optional per-layer list of Dropout2d noise tensors (None entries = draw / skip), used by
         the parity tests to replay the reference's RNG stream."""
+        if drop_noise is None and self.training and input.is_cuda:
+            drop_noise = self._draw_noise(input.shape[0], input.device)
         output = self.initial_block(input)
         for i, layer in enumerate(self.layers):
             if drop_noise is not None and isinstance(layer, non_bottleneck_1d_RAP):
@@ -157,7 +176,6 @@ class UpsamplerBlock(nn.Module):
     def forward(self, input):
         cfg = F_.SampConfig(self.training, _bn_buffers(self.bn), self._cache, 0)
         out = F_.UpFn.apply(input, cfg, self.conv.weight, self.conv.bias, self.bn.weight, self.bn.bias)
-        _tick(self.bn, self.training)
         return out
 
 

@@ -67,8 +67,8 @@ def grad_target(param: torch.Tensor, need: bool):
     return t, t
 
 
-def _bn_struct(w, b, rm, rv) -> L.BnParams:
-    return L.BnParams(_ptr(w), _ptr(b), _ptr(rm), _ptr(rv))
+def _bn_struct(w, b, rm, rv, nbt=None) -> L.BnParams:
+    return L.BnParams(_ptr(w), _ptr(b), _ptr(rm), _ptr(rv), _ptr(nbt))
 
 
 class PackedCache:

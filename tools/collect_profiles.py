@@ -10,7 +10,7 @@ copies = {"bench_step1.json": "bench_step1.json", "bench_step2.json": "bench_ste
           "launches.csv": "step1_launches.csv", "launch_summary.txt": "step1_launch_summary.txt", "gpu.txt": "gpu.txt",
           "parity.jsonl": "parity_pretrained_train_step.jsonl", "trace_counters.txt": "trace_counters.txt",
           "pytest_gpu.txt": "pytest_gpu.txt", "smoke.txt": "smoke.txt"}
-for name in ("h3_c64_fwd", "h3_c64_bwd", "h3_c128_fwd", "h3_c128_bwd", "h3_c16_fwd", "h3_c16_bwd", "wgrad_tc", "small"):
+for name in ("h3_c64_fwd", "h3_c64_bwd", "h3_c128_fwd", "h3_c128_bwd", "h3_c16_fwd", "h3_c16_bwd", "wgrad_tc", "conv_tc", "small"):
     copies[name + ".md"] = "ncu_full_" + name + ".md"
 for src, dst in copies.items():
     s = os.path.join(G, src)

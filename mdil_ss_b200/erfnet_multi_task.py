@@ -30,9 +30,8 @@ class DownsamplerBlock(nn.Module):
         self._cache = F_.PackedCache()
 
     def forward(self, input):
-        cfg = F_.SampConfig(self.training, (self.bn.running_mean, self.bn.running_var), self._cache, 0)
+        cfg = F_.SampConfig(self.training, _rap._bn_buffers(self.bn), self._cache, 0)
         out = F_.DownFn.apply(input, cfg, self.conv.weight, self.conv.bias, self.bn.weight, self.bn.bias)
-        _rap._tick(self.bn, self.training)
         return out
 
 

@@ -214,18 +214,19 @@ bn_act_fused_kernel(const float* __restrict__ u, const double* __restrict__ sums
                     const float* __restrict__ res, float* __restrict__ y, size_t total4, size_t HWC4, int C, long long* nbt) {
   __shared__ __align__(16) float cf[2 * 128];      // scale, shift
   if (blockIdx.x == 0 && threadIdx.x == 0 && train && nbt != nullptr) *nbt += 1;      // nn.BatchNorm2d.num_batches_tracked
+  const double inv_count = 1.0 / count, bessel = count > 1.0 ? count / (count - 1.0) : 1.0;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float mean, var;
     double unbiased = 0.0;
     if (train) {
       double s1 = 0.0, s2 = 0.0;
       for (int p = 0; p < fold; ++p) { s1 += sums[p * C + c]; s2 += sums[ldsum + p * C + c]; }
-      const double m = s1 / count;
-      double v = s2 / count - m * m;
+      const double m = s1 * inv_count;
+      double v = s2 * inv_count - m * m;
       if (v < 0.0) v = 0.0;
       mean = (float)m;
       var = (float)v;
-      unbiased = count > 1.0 ? v * count / (count - 1.0) : v;
+      unbiased = v * bessel;
     } else {
       mean = rm[c];
       var = rv[c];
@@ -362,12 +363,13 @@ bn_bwd_apply_fused_kernel(const float* __restrict__ dy, const float* __restrict_
                           double count, const float* __restrict__ gamma, int fold, float* __restrict__ dgamma,
                           float* __restrict__ dbeta, float* __restrict__ du, size_t total4, size_t HWC4, int C, int split) {
   __shared__ __align__(16) float cf[5 * 128];      // g, k1, k2, mean, invstd
+  const double inv_count = 1.0 / count;             // one fp64 division per thread, off the per-channel dependency chains
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     double sdz = 0.0, sdzu = 0.0;      // fold > 1: sums are [2][fold * C] per (pixel slot, channel)
     for (int p = 0; p < fold; ++p) { sdz += sums[p * C + c]; sdzu += sums[fold * C + p * C + c]; }
     cf[c] = __ldg(gamma + c) * __ldg(stats + C + c);
-    cf[C + c] = (float)(sdz / count);
-    cf[2 * C + c] = (float)(sdzu / count);
+    cf[C + c] = (float)(sdz * inv_count);
+    cf[2 * C + c] = (float)(sdzu * inv_count);
     cf[3 * C + c] = __ldg(stats + c);
     cf[4 * C + c] = __ldg(stats + C + c);
     if (blockIdx.x == 0) {

@@ -106,6 +106,7 @@ def test_gpu_train_forward_backward_matches_reference():
     g = golden("mt_model.npz")
     net, _ = _seeded_sd(int(g["train_seed"]), int(g["train_bn_seed"]))
     net = net.to("cuda").train()
+    counted = {k: int(v) for k, v in net.state_dict().items() if k.endswith("num_batches_tracked")}
     gen = torch.Generator().manual_seed(int(g["train_x_seed"]))
     x = torch.rand(2, 3, 32, 64, generator=gen)
     labels = torch.randint(0, 20, (2, 1, 32, 64), generator=gen)
@@ -133,4 +134,8 @@ def test_gpu_train_forward_backward_matches_reference():
     after = net.state_dict()
     bn_sum = np.array([float(after[str(k)].double().sum()) for k in g["bn_names"]])
     np.testing.assert_allclose(bn_sum, g["bn_sum"], rtol=1e-4, atol=1e-5)
+    # every BatchNorm the step ran through counted one batch (the forward kernels update the buffer), the others none
+    counts = {k: int(v) - counted[k] for k, v in after.items() if k.endswith("num_batches_tracked")}
+    assert counts["encoder.initial_block.bn.num_batches_tracked"] == 1 and set(counts.values()) <= {0, 1}
+    assert sum(counts.values()) >= 30
     assert net.decoder[0].output_conv.weight.grad is None and net.decoder[2].output_conv.weight.grad is None

@@ -9,7 +9,9 @@ copies = {"bench_step1.json": "bench_step1.json", "bench_step2.json": "bench_ste
           "bench_multitask_1024x2048.json": "bench_multitask_1024x2048.json", "bench_reference.json": "bench_reference_arm.json",
           "launches.csv": "step1_launches.csv", "launch_summary.txt": "step1_launch_summary.txt", "gpu.txt": "gpu.txt",
           "parity.jsonl": "parity_pretrained_train_step.jsonl", "trace_counters.txt": "trace_counters.txt",
-          "pytest_gpu.txt": "pytest_gpu.txt", "smoke.txt": "smoke.txt"}
+          "pytest_gpu.txt": "pytest_gpu.txt", "smoke.txt": "smoke.txt", "pytest_gpu_multi.txt": "pytest_gpu_multi.txt"}
+for n in ("step1_2gpu", "step1_4gpu", "step1_8gpu", "step2_2gpu", "step3_8gpu", "multitask_1024x2048_8gpu"):
+    copies[f"bench_{n}.json"] = f"bench_{n}.json"
 for name in ("h3_c64_fwd", "h3_c64_bwd", "h3_c128_fwd", "h3_c128_bwd", "h3_c16_fwd", "h3_c16_bwd", "wgrad_tc", "conv_tc", "small"):
     copies[name + ".md"] = "ncu_full_" + name + ".md"
 for src, dst in copies.items():

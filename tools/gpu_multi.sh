@@ -7,6 +7,8 @@ run() { name=$1; n=$2; shift 2
   python -c "
 import json,sys
 d=json.load(open('gpurun_out/$name.json')); print('$name', d['n_gpus'], round(d['value'],1), round(d['ms_per_step'],2), round(d['e2e']['value'],1), d.get('cuda_graph'), d['clocks']['sm_mhz'], d['clocks']['reasons'])" || tail -3 gpurun_out/$name.err | cut -c1-300; }
+echo '=== multi-GPU tests'; timeout -k 10 -s TERM 300 python -m pytest tests/test_gpu_multi.py -m gpu -q -p no:cacheprovider --tb=short 2>&1 | tail -3 | tee gpurun_out/pytest_gpu_multi.txt
+run bench_step1_2gpu 2 --steps 20 --warmup 5
 run bench_step1_4gpu 4 --steps 20 --warmup 5
 run bench_step1_8gpu 8 --steps 20 --warmup 5
 run bench_step2_2gpu 2 --workload step2 --steps 10 --warmup 3

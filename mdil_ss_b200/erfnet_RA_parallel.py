@@ -12,10 +12,14 @@ non_bottleneck_1d_RAP :67-113, Encoder :123-149, UpsamplerBlock :152-162, Decode
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 
 from . import functional as F_
+
+_PREPACK = os.environ.get("MDIL_PREPACK", "1") != "0"     # A/B switch: weight packing on a side stream at the step start
 
 # Domain selector read by the blocks at call time, exactly like the reference's module-global (:11, :22, :91).
 current_task = 0
@@ -40,6 +44,9 @@ class DownsamplerBlock(nn.Module):
         cfg = F_.SampConfig(self.training, _bn_buffers(bn), self._cache, 0)
         out = F_.DownFn.apply(input, cfg, self.conv.weight, self.conv.bias, bn.weight, bn.bias)
         return out
+
+    def _prepack(self, task):
+        F_.prepack_down(self._cache, 0, self.conv.weight, self.conv.in_channels)
 
 
 class non_bottleneck_1d(nn.Module):
@@ -73,6 +80,12 @@ class non_bottleneck_1d(nn.Module):
                               self.conv3x1_2.weight, self.conv3x1_2.bias, self.conv1x3_2.weight, self.conv1x3_2.bias,
                               self.bn1.weight, self.bn1.bias, self.bn2.weight, self.bn2.bias)
         return out
+
+    def _prepack(self, task):
+        F_.prepack_nb1d(self._cache, 0, False,
+                        (self.conv3x1_1.weight, self.conv3x1_1.bias, self.conv1x3_1.weight, self.conv1x3_1.bias,
+                         self.conv3x1_2.weight, self.conv3x1_2.bias, self.conv1x3_2.weight, self.conv1x3_2.bias,
+                         self.bn1.weight, self.bn1.bias, self.bn2.weight, self.bn2.bias))
 
 
 class non_bottleneck_1d_RAP(nn.Module):
@@ -109,6 +122,14 @@ class non_bottleneck_1d_RAP(nn.Module):
                               bn1.weight, bn1.bias, bn2.weight, bn2.bias,
                               ad1.weight, ad1.bias, ad2.weight, ad2.bias)
         return out
+
+    def _prepack(self, task):
+        bn1, bn2 = self.bns_1[task], self.bns_2[task]
+        ad1, ad2 = self.parallel_conv_1[task], self.parallel_conv_2[task]
+        F_.prepack_nb1d(self._cache, task, True,
+                        (self.conv3x1_1.weight, self.conv3x1_1.bias, self.conv1x3_1.weight, self.conv1x3_1.bias,
+                         self.conv3x1_2.weight, self.conv3x1_2.bias, self.conv1x3_2.weight, self.conv1x3_2.bias,
+                         bn1.weight, bn1.bias, bn2.weight, bn2.bias, ad1.weight, ad1.bias, ad2.weight, ad2.bias))
 
 
 class Encoder(nn.Module):
@@ -158,6 +179,10 @@ class Encoder(nn.Module):
         if drop_noise is None and self.training and input.is_cuda:
             drop_noise = self._draw_noise(input.shape[0], input.device)
         output = self.initial_block(input)
+        join = getattr(self, "_prepack_join", None)
+        if join is not None:       # Net._prepack_async: the other blocks' weight packing ran under the initial block
+            self._prepack_join = None
+            torch.cuda.current_stream(input.device).wait_stream(join)
         for i, layer in enumerate(self.layers):
             if drop_noise is not None and isinstance(layer, non_bottleneck_1d_RAP):
                 output = layer(output, drop_noise[i])
@@ -177,6 +202,9 @@ class UpsamplerBlock(nn.Module):
         cfg = F_.SampConfig(self.training, _bn_buffers(self.bn), self._cache, 0)
         out = F_.UpFn.apply(input, cfg, self.conv.weight, self.conv.bias, self.bn.weight, self.bn.bias)
         return out
+
+    def _prepack(self, task):
+        F_.prepack_up(self._cache, 0, self.conv.weight)
 
 
 class Decoder(nn.Module):
@@ -206,10 +234,27 @@ class Net(nn.Module):
         print('hi, inside erfnet_RA_parallel', current_task, nb_tasks)
         self.encoder = Encoder(nb_tasks)
         self.decoder = nn.ModuleList([Decoder(num_classes[i]) for i in range(nb_tasks)])
+        self.__dict__["_prepack_streams"] = {}     # device -> side stream (shared with nn.DataParallel's replicas)
+
+    def _prepack_async(self, task, device):
+        """Training step: the packed weight copies of every block but the first are refreshed on a side stream, under
+        the initial downsampler, instead of one small launch in front of every block's forward (the optimiser changed
+        all of them).  The blocks' own cache checks then find them current."""
+        streams = self.__dict__.setdefault("_prepack_streams", {})
+        side = streams.get(device)
+        if side is None:
+            side = streams[device] = torch.cuda.Stream(device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            for layer in list(self.encoder.layers) + list(self.decoder[task].layers):
+                layer._prepack(task)
+        self.encoder._prepack_join = side
 
     def forward(self, input, task, drop_noise=None):
         global current_task
         current_task = task
+        if self.training and input.is_cuda and torch.is_grad_enabled() and _PREPACK:
+            self._prepack_async(task, input.device)
         if drop_noise is not None:
             output = self.encoder(input, drop_noise=drop_noise)
         else:

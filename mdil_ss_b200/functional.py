@@ -132,6 +132,50 @@ def _nb1d_weights(params, cfg: Nb1dConfig) -> L.Nb1dWeights:
     return w
 
 
+def prepack_nb1d(cache: PackedCache, cache_key, has_adapter: bool, params) -> None:
+    """Refresh the packed weights of a nb1d block ahead of its forward (same cache key, tensors and pack call as
+    Nb1dFn.forward, which then finds them current).  The packing launch depends only on the channel counts; it goes to the
+    current stream -- erfnet_RA_parallel.Net runs it on a side stream under the first layers of the step."""
+    lib = L.lib()
+    w0 = params[0]
+    c = int(w0.shape[0])
+    cfg = Nb1dConfig(1, has_adapter, False, (None, None, None), (None, None, None), cache, cache_key)
+    desc = L.Nb1dDesc(1, 4, 4, c, 1, int(has_adapter), 0, 0, BN_EPS, BN_MOMENTUM)
+    with torch.cuda.device_of(w0):
+        wts = _nb1d_weights(params, cfg)
+        conv_params = list(params[:8:2]) + (list(params[12:16:2]) if has_adapter else [])
+
+        def pack(buf):
+            L.check(lib.mdil_nb1d_pack(C.byref(desc), C.byref(wts), buf.data_ptr(), _stream()), "mdil_nb1d_pack")
+
+        cache.get(cache_key, conv_params, int(lib.mdil_nb1d_packed_floats(c)), pack)
+
+
+def prepack_down(cache: PackedCache, cache_key, conv_w, cin: int) -> None:
+    """As prepack_nb1d for DownFn (the packed layouts depend on the channel counts and the input's row stride only)."""
+    lib = L.lib()
+    cout = int(conv_w.shape[0]) + cin
+    ldin = cin if cin % 4 == 0 else 4
+    desc = L.DownDesc(1, 4, 4, cin, cout, ldin, 0, 0, BN_EPS, BN_MOMENTUM)
+    with torch.cuda.device_of(conv_w):
+        def pack(buf):
+            L.check(lib.mdil_down_pack(C.byref(desc), conv_w.data_ptr(), buf.data_ptr(), _stream()), "mdil_down_pack")
+
+        cache.get(cache_key, [conv_w], int(lib.mdil_down_packed_floats(C.byref(desc))), pack)
+
+
+def prepack_up(cache: PackedCache, cache_key, conv_w) -> None:
+    """As prepack_nb1d for UpFn."""
+    lib = L.lib()
+    cin, cout = int(conv_w.shape[0]), int(conv_w.shape[1])
+    desc = L.UpDesc(1, 4, 4, cin, cout, 0, 0, BN_EPS, BN_MOMENTUM)
+    with torch.cuda.device_of(conv_w):
+        def pack(buf):
+            L.check(lib.mdil_up_pack(C.byref(desc), conv_w.data_ptr(), buf.data_ptr(), _stream()), "mdil_up_pack")
+
+        cache.get(cache_key, [conv_w], int(lib.mdil_up_packed_floats(C.byref(desc))), pack)
+
+
 class Nb1dFn(torch.autograd.Function):
     """non_bottleneck_1d_RAP.forward / non_bottleneck_1d.forward (models/erfnet_RA_parallel.py:90-113, 48-64).
 

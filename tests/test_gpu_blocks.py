@@ -1,6 +1,8 @@
 """GPU: every block kernel (forward, backward, BatchNorm buffer updates) against the oracle on the same seeded
 inputs, through the product modules -> ctypes -> C ABI.  Tolerance: north star's 1e-3 relative fp32 (max-norm);
 observed errors are ~1e-6."""
+import os
+
 import pytest
 import torch
 
@@ -262,3 +264,16 @@ def test_cpu_tensor_is_rejected():
     mod = M.non_bottleneck_1d(16, 0, 1)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         mod(torch.zeros(1, 16, 4, 4))
+
+
+def test_round1_kernels_behind_the_switches_still_match():
+    """The warp-level / FFMA sampler kernels, the fp32 backward workspaces and the two-kernel head backward are the product
+    path for shapes the tcgen05 kernels do not cover and the A/B references of DESIGN.md: the block tests must stay green
+    with every switch thrown (the switches are read once per process, hence the subprocess)."""
+    import subprocess
+    import sys
+    env = dict(os.environ, MDIL_CONV_TC="0", MDIL_WGRAD_GATHER="0", MDIL_S16="0", MDIL_HEAD_FUSED="0", MDIL_PREPACK="0")
+    sel = "downsampler or upsampler or output_conv or (nb1d_block and 64)"
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider",
+                        "-k", sel], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-1000:]

@@ -11,6 +11,14 @@
 // are then the activation chunks j-1, j, j+1 already in the shared-memory ring.  Accumulators (3 x [C x C] fp32)
 // stay in TMEM for the whole life of the persistent CTA and leave through vectorised red.global.add.v4.f32.
 //
+// Gathered jobs (launch_wgrad_gather_tc, kernel instantiation <64, 18>): the weight gradients of the samplers' strided and
+// transposed 3x3 convolutions (models/erfnet_RA_parallel.py:24-45, 160-172) are one-tap jobs of the same kernel whose
+// producers gather activation / gradient pixels through ConvGeom's affine maps (pixel = v * stride + tap offset, zeros
+// outside the tensor) -- one launch per layer, one job per (tap, 64-channel block of CIN).  Narrow operands are stacked
+// into 16- or 4-channel slots of the 64-channel operand row, each slot with its own tap offset: the nine taps of the
+// 3 -> 13 convolution form ONE job (stacked along M), the taps of the 64 -> 16 upsampler that read the same activation
+// pixel share a job (their gradient pixels stacked along N).  G may arrive pre-split (S16 format, g_split).
+//
 // Warp roles: warps 0-15 producers (four groups of 4 warps fill ring stages round-robin; the producers are bound by the
 // latency of their own instruction stream, so warp count is what buys throughput), warps 16-18: one MMA issuer per tap.
 #include <cuda_bf16.h>

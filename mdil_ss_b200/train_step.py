@@ -182,7 +182,7 @@ class MultiTaskTrainer:
 
 
 class GraphedStep:
-    """One training iteration captured in a CUDA graph and replayed: ~410 kernel launches, the weight
+    """One training iteration captured in a CUDA graph and replayed: ~300 kernel launches, the weight
     re-packing, the gradient all-reduce and the fused Adam become ONE host call, which takes the Python / launch overhead
     (~10 ms per step from idle) off the critical path -- what limits end-to-end scaling when 8 ranks share one host.
 

@@ -567,6 +567,9 @@ static int launch_t(const ConvGeom& g, const Plan& pl, const float* A, const voi
   using K = Cfg<CINP, NCLS, NCO>;
   static_assert(K::SMEM_BYTES <= 227 * 1024, "conv_tc shared memory budget");
   static_assert(K::NKC * K::NBUF <= 16 && NCO <= 128 && 8 * 2 * NCO * 4 <= (int)K::BUF_BYTES && K::ACCW * 2 <= 512, "conv_tc layout");
+  static_assert(N_LOAD >= IN_MAX && INROWS <= IN_MAX && TU * PV == 128 && OFF_PIXTAB + 8 * IN_MAX <= K::HDR_BYTES &&
+                    NTHREADS == (W_PROD + 1) * 32 && NCO % 16 == 0,
+                "conv_tc role mapping / tile geometry");
   Args a;
   memset(&a, 0, sizeof(a));
   a.A = A; a.wimg = wimg; a.bias = bias; a.out = out; a.sums = sums;

@@ -12,7 +12,7 @@ copies = {"bench_step1.json": "bench_step1.json", "bench_step2.json": "bench_ste
           "pytest_gpu.txt": "pytest_gpu.txt", "smoke.txt": "smoke.txt", "pytest_gpu_multi.txt": "pytest_gpu_multi.txt"}
 for n in ("step1_2gpu", "step1_4gpu", "step1_8gpu", "step2_2gpu", "step3_8gpu", "multitask_1024x2048_8gpu"):
     copies[f"bench_{n}.json"] = f"bench_{n}.json"
-for name in ("h3_c64_fwd", "h3_c64_bwd", "h3_c128_fwd", "h3_c128_bwd", "h3_c16_fwd", "h3_c16_bwd", "wgrad_tc", "conv_tc", "small"):
+for name in ("h3_c64_fwd", "h3_c64_bwd", "h3_c128_fwd", "h3_c128_bwd", "h3_c16_fwd", "h3_c16_bwd", "wgrad_tc", "conv_tc", "small", "head", "bn_bwd"):
     copies[name + ".md"] = "ncu_full_" + name + ".md"
 for src, dst in copies.items():
     s = os.path.join(G, src)

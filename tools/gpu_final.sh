@@ -29,6 +29,8 @@ cap h3_c128_bwd pair_h3_kernel 42 2 drop
 cap h3_c64_bwd pair_h3_kernel 58 2 keep
 cap wgrad_tc wgrad_tc_kernel 0 8 drop
 cap conv_tc "^conv_tc_kernel" 0 9 drop
-cap small "outconv|ce2d|bn_bwd_apply_fused|bn_act_fused|stats_kernel" 0 12 drop
+cap small "bn_act_fused|stats_kernel" 0 12 drop
+cap head "outconv|ce2d_phase" 0 4 drop
+cap bn_bwd "bn_bwd_apply_fused|stats_kernel|bn_act_fused" 30 8 drop
 echo "=== trace"; MDIL_TC_TRACE=1 timeout -s KILL 120 python tools/trace_tc.py 2>&1 | grep -v "^hi" | grep -A3 "pair_h3\|wgrad_tc" > gpurun_out/trace_counters.txt; head -8 gpurun_out/trace_counters.txt
 du -sh gpurun_out

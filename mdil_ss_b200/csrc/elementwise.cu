@@ -53,25 +53,33 @@ stats_kernel(const float* __restrict__ x, const float* __restrict__ y, const flo
     mean = ldg4(stats + c4 * 4);
     istd = ldg4(stats + C + c4 * 4);
   }
-  for (size_t p = (size_t)blockIdx.x * lanes + lane; p < P; p += (size_t)gridDim.x * lanes) {
+  // two pixels per iteration, all of their loads issued before the first use: the launch runs 4 CTAs per SM (more CTAs
+  // mean more same-address fp64 atomics at the end) and needs the bytes in flight to cover the HBM latency
+  const size_t stride = (size_t)gridDim.x * lanes;
+  for (size_t p = (size_t)blockIdx.x * lanes + lane; p < P; p += 2 * stride) {
+    const size_t q = p + stride;
+    const bool two = q < P;
     float4 v = ldg4(x + p * C + c4 * 4);
+    float4 v2 = two ? ldg4(x + q * C + c4 * 4) : make4(0.f);
     if (MODE == 0) {
-      s1.x += v.x; s1.y += v.y; s1.z += v.z; s1.w += v.w;
-      s2.x += v.x * v.x; s2.y += v.y * v.y; s2.z += v.z * v.z; s2.w += v.w * v.w;
+      s1.x += v.x + v2.x; s1.y += v.y + v2.y; s1.z += v.z + v2.z; s1.w += v.w + v2.w;
+      s2.x += v.x * v.x + v2.x * v2.x; s2.y += v.y * v.y + v2.y * v2.y;
+      s2.z += v.z * v.z + v2.z * v2.z; s2.w += v.w * v.w + v2.w * v2.w;
     } else {
-      if (y != nullptr) {
-        float4 yy = ldg4(y + p * C + c4 * 4);
-        v.x = yy.x > 0.f ? v.x : 0.f; v.y = yy.y > 0.f ? v.y : 0.f;
-        v.z = yy.z > 0.f ? v.z : 0.f; v.w = yy.w > 0.f ? v.w : 0.f;
-      }
-      if (drop != nullptr) {
-        float4 d = ldg4(drop + (p / HW) * C + c4 * 4);
-        v.x *= d.x; v.y *= d.y; v.z *= d.z; v.w *= d.w;
-      }
-      float4 uu = ldg4(u + p * C + c4 * 4);
-      s1.x += v.x; s1.y += v.y; s1.z += v.z; s1.w += v.w;
-      s2.x += v.x * ((uu.x - mean.x) * istd.x); s2.y += v.y * ((uu.y - mean.y) * istd.y);
-      s2.z += v.z * ((uu.z - mean.z) * istd.z); s2.w += v.w * ((uu.w - mean.w) * istd.w);
+      float4 yy = make4(1.f), yy2 = make4(1.f), d = make4(1.f), d2 = make4(1.f);
+      if (y != nullptr) { yy = ldg4(y + p * C + c4 * 4); if (two) yy2 = ldg4(y + q * C + c4 * 4); }
+      if (drop != nullptr) { d = ldg4(drop + (p / HW) * C + c4 * 4); if (two) d2 = ldg4(drop + (q / HW) * C + c4 * 4); }
+      const float4 uu = ldg4(u + p * C + c4 * 4);
+      const float4 uu2 = two ? ldg4(u + q * C + c4 * 4) : make4(0.f);
+      v.x = yy.x > 0.f ? v.x * d.x : 0.f; v.y = yy.y > 0.f ? v.y * d.y : 0.f;
+      v.z = yy.z > 0.f ? v.z * d.z : 0.f; v.w = yy.w > 0.f ? v.w * d.w : 0.f;
+      v2.x = yy2.x > 0.f ? v2.x * d2.x : 0.f; v2.y = yy2.y > 0.f ? v2.y * d2.y : 0.f;
+      v2.z = yy2.z > 0.f ? v2.z * d2.z : 0.f; v2.w = yy2.w > 0.f ? v2.w * d2.w : 0.f;
+      s1.x += v.x + v2.x; s1.y += v.y + v2.y; s1.z += v.z + v2.z; s1.w += v.w + v2.w;
+      s2.x += v.x * ((uu.x - mean.x) * istd.x) + v2.x * ((uu2.x - mean.x) * istd.x);
+      s2.y += v.y * ((uu.y - mean.y) * istd.y) + v2.y * ((uu2.y - mean.y) * istd.y);
+      s2.z += v.z * ((uu.z - mean.z) * istd.z) + v2.z * ((uu2.z - mean.z) * istd.z);
+      s2.w += v.w * ((uu.w - mean.w) * istd.w) + v2.w * ((uu2.w - mean.w) * istd.w);
     }
   }
   double* a = sh + (size_t)lane * C + c4 * 4;

@@ -239,3 +239,40 @@ def test_lr_factor_follows_lambda_lr():
         ta.step()
         for p, q in zip(pa, pb):
             assert torch.allclose(p, q, rtol=1e-6, atol=1e-8)
+
+
+def test_dropout_noise_of_a_step_comes_from_one_draw():
+    """Encoder._draw_noise (host logic, device-independent): one uniform draw yields F.dropout2d's [N, C, 1, 1] noise for
+    every block with p > 0 (values 0 or 1 / (1 - p), models/erfnet_RA_parallel.py:61,110), None for the samplers."""
+    from mdil_ss_b200 import erfnet_RA_parallel as M
+    enc = M.Encoder(1)
+    torch.manual_seed(5)
+    noise = enc._draw_noise(3, torch.device("cpu"))
+    assert len(noise) == len(enc.layers)
+    seen = 0
+    for layer, t in zip(enc.layers, noise):
+        if isinstance(layer, M.non_bottleneck_1d_RAP) and layer.dropout.p > 0:
+            c = layer.bns_1[0].num_features
+            assert tuple(t.shape) == (3, c, 1, 1) and t.is_contiguous()
+            keep = 1.0 - layer.dropout.p
+            vals = set(torch.unique(t).tolist())
+            assert all(abs(v) < 1e-12 or abs(v - 1.0 / keep) < 1e-5 for v in vals), vals
+            seen += 1
+        else:
+            assert t is None
+    assert seen == 13
+    again = enc._draw_noise(3, torch.device("cpu"))        # the plan is cached, the draw is not
+    assert any(not torch.equal(a, b) for a, b in zip(noise, again) if a is not None)
+    # keep-rate of the p = 0.3 blocks over many channels
+    big = torch.cat([enc._draw_noise(64, torch.device("cpu"))[-1].flatten() for _ in range(4)])
+    assert abs(float((big > 0).float().mean()) - 0.7) < 0.02
+
+
+def test_bn_params_struct_matches_the_header():
+    """mdil_bn_params (include/mdil_b200.h) and its ctypes mirror: five pointers, num_batches_tracked last."""
+    from mdil_ss_b200 import _lib as L
+    hdr = open(os.path.join(REPO, "include", "mdil_b200.h")).read()
+    body = hdr[hdr.index("typedef struct {\n  const float* weight;"):hdr.index("} mdil_bn_params;")]
+    names = re.findall(r"\*\s*(\w+);", body)
+    assert names == [n for n, _ in L.BnParams._fields_] == ["weight", "bias", "running_mean", "running_var", "num_batches_tracked"]
+    assert ctypes.sizeof(L.BnParams) == 5 * ctypes.sizeof(ctypes.c_void_p)
